@@ -1,0 +1,189 @@
+/*
+ * rt_b200.h -- C ABI of librt_b200.so: the B200-native `render` hot path of
+ * jilinzheng/RaytracingInCUDA behind plain pointers and sizes.
+ *
+ * The reference has no library boundary: its hot path is entered at one place, the launch pair
+ *     init_rng<<<g,b>>>(W, H, states)                                   GF main.cu:328
+ *     render  <<<g,b>>>(pixel_buffer, cam, d_world, d_rand_states)      GF main.cu:335
+ * preceded by the host scene build + upload (GF main.cu:142-321) and followed by the PPM writer
+ * (GF main.cu:347-379).  ("GF" = src/GlobalFloatCUDAInOneWeekend, "GD" = src/GlobalDoubleCUDAInOneWeekend.)
+ * Each entry point below names the reference lines it stands in for.  A maintainer of the
+ * reference replaces those lines with the calls shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success, a cudaError_t value (>0) for CUDA failures,
+ * or an RT_E* code (<0); no exceptions cross the boundary; the caller owns every buffer; one
+ * rt_ctx per device, used from one host thread at a time.  Buffers marked "host or device" are
+ * classified with cudaPointerGetAttributes.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+enum {
+    RT_OK = 0,
+    RT_EINVAL = -1,      /* bad argument */
+    RT_ENOSCENE = -2,    /* render/primary called before rt_upload_scene */
+    RT_ENOMEM = -3,      /* host allocation failed */
+    RT_EIO = -4,         /* file could not be opened / written */
+    RT_ENODEVICE = -5,   /* no CUDA device / not an sm_100 part */
+    RT_EPRECISION = -6   /* scene precision does not match the call */
+};
+
+enum { RT_LAMBERTIAN = 0, RT_METAL = 1, RT_DIELECTRIC = 2 };   /* GF material.h:11-15 */
+
+/* One sphere + its material: the reference's `sphere` (GF hittable.h:29-37) and `material`
+ * (GF material.h:18-34) flattened to the fields the device code reads.  40 bytes. */
+typedef struct rt_slot {
+    float cx, cy, cz, r;
+    int32_t type;
+    float albedo[3];     /* lambertian, metal */
+    float fuzz;          /* metal */
+    float ri;            /* dielectric */
+} rt_slot;
+
+typedef struct rt_slot64 {                                      /* GD hittable.h / material.h */
+    double cx, cy, cz, r;
+    int32_t type, pad;
+    double albedo[3];
+    double fuzz;
+    double ri;
+} rt_slot64;
+
+/* The fields of the reference `camera` (GF camera.h:10-31) that its kernels read. */
+typedef struct rt_camera {
+    int32_t width, height, spp, max_depth;
+    float scale;                 /* pixel_samples_scale */
+    float center[3];
+    float pixel00[3];
+    float du[3], dv[3];          /* pixel_delta_u / pixel_delta_v */
+    float defocus_angle;
+    float disk_u[3], disk_v[3];  /* defocus_disk_u / defocus_disk_v */
+} rt_camera;
+
+typedef struct rt_camera64 {
+    int32_t width, height, spp, max_depth;
+    double scale;
+    double center[3];
+    double pixel00[3];
+    double du[3], dv[3];
+    double defocus_angle;
+    double disk_u[3], disk_v[3];
+} rt_camera64;
+
+enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
+enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1 };
+
+/* Per-call options.  Zero-initialise, then set what you need (rt_opts_default does that). */
+typedef struct rt_opts {
+    uint64_t seed;        /* Philox key; default 1227 (the reference's curand seed, GF rtweekend.h:49) */
+    int32_t split;        /* RT_SPLIT_*: which part of the frame this context renders */
+    int32_t rank, world;  /* this context's index / number of partitions (1 = whole frame) */
+    int32_t tile_rows;    /* RT_SPLIT_ROWS: rows per interleaved tile (default 8) */
+    int32_t accel;        /* RT_ACCEL_* */
+    int32_t threads;      /* the reference's --threads; accepted and ignored by the persistent kernel */
+    int32_t reserved[8];
+} rt_opts;
+
+typedef struct rt_stats {
+    uint64_t paths;          /* path-samples traced by the last render call on this context */
+    uint64_t segments;       /* hit_world calls (ray segments) of the last render call */
+    uint64_t sphere_tests;   /* sphere tests (segments x slots for the linear scan; counted for LBVH) */
+    uint64_t node_visits;    /* LBVH node visits (0 for the linear scan) */
+    float render_ms;         /* CUDA-event time of the render kernels of the last call */
+    float trace_ms;          /* ... of the path-tracing kernel alone */
+    int32_t launches;        /* kernels launched by the last call */
+    int32_t chunks;          /* accumulation chunks of the last call */
+    int32_t grid, block;     /* launch shape of the path-tracing kernel */
+    int32_t regs, smem_bytes;
+} rt_stats;
+
+/* ------------------------------------------------------------------ host side (no GPU) ---- */
+
+/* Scene generator, bit-exact with GF main.cu:142-298 (host RNG GF rtweekend.h:22-30).
+ * scene_id 1, 2, anything else -> scene 3 (GF main.cu:241).  Returns the slot count; writes at
+ * most `capacity` slots when `out` is non-NULL. */
+int rt_scene_generate(int scene_id, rt_slot *out, int capacity);
+int rt_scene_generate64(int scene_id, rt_slot64 *out, int capacity);      /* GD main.cu:142-298 */
+/* Scaled scene of BASELINE config 5 (not in the reference): same per-cell generator over the
+ * grid [-half, half)^2; half = 158 gives 99 860 slots. */
+int rt_scene_generate_scaled(int half, rt_slot *out, int capacity);
+
+/* camera::initialize() (GF camera.h:33-68) for the fixed view of GF main.cu:100-124. */
+int rt_camera_init(rt_camera *cam, int width, int height, int spp, int max_depth);
+int rt_camera_init64(rt_camera64 *cam, int width, int height, int spp, int max_depth);
+
+void rt_opts_default(rt_opts *opts);
+
+/* Number of accumulation chunks for (width, height, spp): depends on nothing else, so the image
+ * is the same for every GPU count and launch shape. */
+int rt_num_chunks(int width, int height, int spp);
+
+/* Rows rendered by `rank` of `world` under RT_SPLIT_ROWS, ascending.  Returns the count; writes
+ * at most `capacity` row indices when `rows` is non-NULL. */
+int rt_partition_rows(int height, int tile_rows, int rank, int world, int32_t *rows, int capacity);
+/* Chunks [*c0, *c1) rendered by `rank` of `world` under RT_SPLIT_SPP. */
+int rt_partition_chunks(int chunks, int rank, int world, int32_t *c0, int32_t *c1);
+
+/* PPM writer, byte-identical with GF main.cu:361-378 (P3, int(256*clamp(x,0,0.999))). */
+int rt_ppm_write(const char *path, const float *rgb, int width, int height);
+int rt_ppm_write64(const char *path, const double *rgb, int width, int height);
+int rt_ppm_quantise(const float *rgb, size_t n, uint8_t *out);
+
+const char *rt_error_string(int code);
+int rt_abi_version(void);
+
+/* ------------------------------------------------------------------ device side ----------- */
+typedef struct rt_ctx rt_ctx;
+
+/* Replaces cudaSetDevice + the event/buffer setup of GF main.cu:81-95,133-134. */
+int rt_create(int device, rt_ctx **ctx);
+int rt_destroy(rt_ctx *ctx);
+/* Optional: run on the caller's stream (a cudaStream_t) instead of the context's own. */
+int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
+
+/* Replaces the three cudaMemcpy + two pointer-fix-up kernels of GF main.cu:300-321: the slots are
+ * repacked SoA (float4 centre/radius, float4 albedo/param, int type) into one device blob that
+ * the kernels stage into shared memory with a TMA bulk copy. */
+int rt_upload_scene(rt_ctx *ctx, const rt_slot *slots, int n);
+int rt_upload_scene64(rt_ctx *ctx, const rt_slot64 *slots, int n);
+
+/* Replaces init_rng + render (GF main.cu:326-341).  out_rgb: gamma-encoded floats, 3 per pixel,
+ * row-major, row 0 = top (the reference's pixel_buffer layout); host or device.
+ *   split NONE: width*height*3 floats.
+ *   split ROWS: only this rank's rows, compacted in ascending row order (rt_partition_rows).
+ *   split SPP : not valid here -- use rt_render_partials + rt_finalize.
+ * render_ms (optional) receives the CUDA-event time of the kernels, the reference's
+ * render_only timer (GF main.cu:334-341). */
+int rt_render(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, float *out_rgb, float *render_ms);
+int rt_render64(rt_ctx *ctx, const rt_camera64 *cam, const rt_opts *opts, double *out_rgb, float *render_ms);
+
+/* spp-split building blocks.  rt_render_partials writes, for this rank's chunks c in [c0,c1) and
+ * every pixel p, the linear (pre-gamma) chunk sum as 4 floats {r,g,b,0} at
+ * partials[((c-c0)*width*height + p)*4]; partials is a DEVICE buffer of (c1-c0)*width*height*4
+ * floats.  rt_finalize adds `chunks` such planes in chunk order, scales by 1/spp, applies gamma
+ * (GF camera.h:167-171) and writes width*height*3 floats to out_rgb (host or device). */
+int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, float *partials_dev,
+                       float *render_ms);
+int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, int chunks,
+                float *out_rgb, float *finalize_ms);
+
+/* Deterministic primary-ray pass: for every pixel the ray o = cam.center,
+ * d = fma(j, dv, fma(i, du, pixel00)) - o goes through the reference's hit_world
+ * (GF hittable.h:80-98).  ids: slot index or -1; t: hit distance or +inf.  Host or device. */
+int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t);
+int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t);
+
+int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,233 @@
+// rt_device.cuh -- device-side building blocks of the B200 render path: explicit-rounding
+// arithmetic, Philox4x32-10, the TMA bulk scene stage, and the closest-hit scan.
+//
+// Arithmetic contract.  The reference's results are fixed by where ptxas
+// fused multiplies and adds in its render kernel (sm_100 SASS of GF hittable.h:40-66:
+// FADD x3, FMUL+FFMA+FFMA for h, FMUL+FFMA+FFMA for |oc|^2, FFMA(-r,r,q), FMUL a*c,
+// FFMA(h,h,-m)).  Here every operation that matters is spelled with a round-to-nearest intrinsic
+// so no compiler version can move a rounding; the file is also compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt {
+
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Num;
+
+template <> struct Num<float> {
+    using vec4 = float4;
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float tmin() { return 0.001f; }            // (float)0.001, GF camera.h:87
+    static __device__ __forceinline__ float near_zero() { return 1e-6f; }        // GF vec3.h:50
+    static __device__ __forceinline__ float unit_min() { return 1e-8f; }         // GF vec3.h:124
+    static constexpr int words_per_uniform = 1;
+    // curand_uniform: x * 2^-32 + 2^-33, in (0,1]  (curand_uniform.h:69-72)
+    static __device__ __forceinline__ float uniform(uint32_t x, uint32_t) {
+        return __fmaf_rn(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    }
+};
+
+template <> struct Num<double> {
+    using vec4 = double4;
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double rcp(double a) { return __drcp_rn(a); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double tmin() { return 0.001; }
+    static __device__ __forceinline__ double near_zero() { return 1e-8; }        // GD vec3.h:50
+    static __device__ __forceinline__ double unit_min() { return 1e-160; }       // GD vec3.h:125
+    static constexpr int words_per_uniform = 2;
+    // curand_uniform_double for 2 words: (x ^ (y << 21)) * 2^-53 + 2^-54  (curand_uniform.h:101-106)
+    static __device__ __forceinline__ double uniform(uint32_t x, uint32_t y) {
+        const unsigned long long z = (unsigned long long)x ^ ((unsigned long long)y << 21);
+        return __dadd_rn(__dmul_rn(__ull2double_rn(z), 1.1102230246251565e-16), 1.1102230246251565e-16 / 2.0);
+    }
+};
+
+template <typename T> struct Vec3 { T x, y, z; };
+
+// dot() of the reference as compiled: fma(u.z, v.z, fma(u.x, v.x, u.y * v.y))  (GF vec3.h:93-97)
+template <typename T>
+__device__ __forceinline__ T dot3(const Vec3<T> &u, const Vec3<T> &v) {
+    using N = Num<T>;
+    return N::fma(u.z, v.z, N::fma(u.x, v.x, N::mul(u.y, v.y)));
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (pixel, sample, dimension, block), key = seed.
+struct Philox {
+    uint32_t c0, c1, c2, k0, k1;      // c3 (block) is supplied per call
+    uint32_t w[4];
+    __device__ __forceinline__ void open(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel,
+                                         uint32_t sample, uint32_t dim) {
+        c0 = pixel; c1 = sample; c2 = dim; k0 = seed_lo; k1 = seed_hi;
+    }
+    __device__ __forceinline__ void block(uint32_t blk) {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = blk, ka = k0, kb = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t y0 = hi1 ^ x1 ^ ka, y2 = hi0 ^ x3 ^ kb;
+            x0 = y0; x1 = lo1; x2 = y2; x3 = lo0;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Scene blob as uploaded by rt_upload_scene: one contiguous, 16-byte aligned device buffer
+//   [vec4 geom[n_pad]]   centre.xyz, radius            (the only array the scan reads)
+//   [vec4 matl[n_pad]]   albedo.xyz, param (fuzz for metal, refraction index for dielectric)
+//   [int  type[n_pad4]]
+// staged into shared memory by one thread with cp.async.bulk + an mbarrier (TMA bulk copy).
+template <typename T> struct SceneView {
+    const typename Num<T>::vec4 *geom;
+    const typename Num<T>::vec4 *matl;
+    const int *type;
+    int n;
+};
+
+struct SceneBlob {
+    const void *base;       // device pointer
+    uint32_t bytes;         // multiple of 16
+    uint32_t matl_off, type_off;
+    int n;
+};
+
+template <typename T>
+__device__ __forceinline__ SceneView<T> view_of(const void *base, const SceneBlob &b) {
+    SceneView<T> v;
+    const char *p = static_cast<const char *>(base);
+    v.geom = reinterpret_cast<const typename Num<T>::vec4 *>(p);
+    v.matl = reinterpret_cast<const typename Num<T>::vec4 *>(p + b.matl_off);
+    v.type = reinterpret_cast<const int *>(p + b.type_off);
+    v.n = b.n;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// global -> shared TMA bulk copy of `bytes` (multiple of 16), completion on `bar`.
+// Must be called by ALL threads of the CTA (it contains the CTA barriers).
+__device__ __forceinline__ void stage_scene(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        uint32_t off = 0;
+        while (off < bytes) {
+            const uint32_t piece = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(static_cast<char *>(smem_dst) + off)),
+                "l"(static_cast<const char *>(gmem_src) + off), "r"(piece), "r"(bar_a)
+                : "memory");
+            off += piece;
+        }
+    }
+    // every thread waits for phase 0 of the barrier
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a)
+            : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// hit_world (GF hittable.h:80-98) as a two-phase scan.
+//  phase 1: for every slot, the discriminant exactly as the reference computes it; slots with
+//           disc >= 0 (0.4 % of tests) are appended to a per-thread candidate list in shared
+//           memory -- no sqrt/div and almost no divergence in the hot loop.
+//  phase 2: candidates are revisited in slot order with the reference's root logic and a
+//           shrinking tmax, so the result (slot id, t) is the one the reference's loop produces:
+//           strict tmin < t < closest, lowest slot wins ties.
+// `cand` points at this thread's column of a [CAND_CAP][blockDim.x] uint16 array.
+constexpr int CAND_CAP = 24;
+
+template <typename T> struct Hit { T t; int id; };
+
+template <typename T>
+__device__ __forceinline__ void resolve_candidates(const SceneView<T> &sc, const Vec3<T> &o, const Vec3<T> &d,
+                                                   T a, const unsigned short *cand, int stride, int count,
+                                                   Hit<T> &hit) {
+    using N = Num<T>;
+    for (int k = 0; k < count; ++k) {
+        const int id = cand[k * stride];
+        const typename N::vec4 s = sc.geom[id];
+        const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
+        const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
+        const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
+        const T c = N::fma(-s.w, s.w, q);
+        const T disc = N::fma(h, h, -N::mul(a, c));
+        const T sq = N::sqrt(disc);
+        T root = N::div(N::sub(h, sq), a);
+        if (!(N::tmin() < root && root < hit.t)) {
+            root = N::div(N::add(h, sq), a);
+            if (!(N::tmin() < root && root < hit.t)) continue;
+        }
+        hit.t = root;
+        hit.id = id;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ Hit<T> closest_hit(const SceneView<T> &sc, const Vec3<T> &o, const Vec3<T> &d,
+                                              unsigned short *cand, int stride) {
+    using N = Num<T>;
+    const T a = dot3(d, d);                                     // GF hittable.h:42
+    Hit<T> hit;
+    hit.t = N::inf();
+    hit.id = -1;
+    int count = 0;
+    const int n = sc.n;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const typename N::vec4 s = sc.geom[i];
+        const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
+        const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
+        const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
+        const T c = N::fma(-s.w, s.w, q);
+        const T disc = N::fma(h, h, -N::mul(a, c));
+        if (!(disc < T(0))) {                                   // GF hittable.h:47
+            cand[count * stride] = static_cast<unsigned short>(i);
+            if (++count == CAND_CAP) {
+                resolve_candidates(sc, o, d, a, cand, stride, count, hit);
+                count = 0;
+            }
+        }
+    }
+    resolve_candidates(sc, o, d, a, cand, stride, count, hit);
+    return hit;
+}
+
+}  // namespace rt

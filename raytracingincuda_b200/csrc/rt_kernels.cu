@@ -1,0 +1,787 @@
+// rt_kernels.cu -- the sm_100a kernels of the render path and the device half of the C ABI.
+//
+//   trace_kernel     persistent-thread path tracer.  One lane = one path at a time; a lane whose
+//                    path ends regenerates the next sample of its (pixel, chunk) job in place, a
+//                    lane whose job ends pulls the next job from a global queue with one
+//                    warp-aggregated atomic (ballot + popc), so all 32 lanes stay inside the
+//                    sphere scan.  Replaces init_rng + render (GF rtweekend.h:43-50,
+//                    GF camera.h:78-172).
+//   finalize_kernel  sums the chunk partials in chunk order, scales, gamma-encodes and writes
+//                    the frame with 16-byte vector stores (GF camera.h:167-171, color.h:10-13).
+//   primary_kernel   deterministic primary-ray (slot id, t) pass through the same closest-hit
+//                    routine (parity probe for GF hittable.h:80-98).
+#include "rt_b200.h"
+#include "rt_device.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace rt {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TRACE_BLOCK = 256;
+
+template <typename T> struct DevCamera {
+    Vec3<T> center, pixel00, du, dv, disk_u, disk_v;
+    T defocus_angle;
+    T scale;
+};
+
+template <typename T> struct TraceArgs {
+    DevCamera<T> cam;
+    SceneBlob scene;
+    uint32_t seed_lo, seed_hi;
+    int spp, max_depth;
+    int width;
+    int tile_rows, rank, world;        // local row -> global row (world == 1: identity)
+    int chunks, c_begin;               // C and the first chunk of this launch
+    unsigned long long pix_local;      // pixels rendered by this launch
+    unsigned long long total_jobs;     // (c_end - c_begin) * pix_local
+    typename Num<T>::vec4 *partial;    // [job]
+    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths
+};
+
+// ------------------------------------------------------------------------------------------
+template <typename T> struct PathState {
+    Vec3<T> o, d, att;
+    T puy;                // y of the normalised PRIMARY direction (sky term, GF camera.h:121)
+};
+
+// get_ray (GF camera.h:145-155) with Philox dimension 0 of (pixel, sample)
+template <typename T>
+__device__ __forceinline__ void camera_ray(const TraceArgs<T> &A, int i, int j, uint32_t pixel, uint32_t sample,
+                                           PathState<T> &ps) {
+    using N = Num<T>;
+    Philox ph;
+    ph.open(A.seed_lo, A.seed_hi, pixel, sample, 0u);
+    ph.block(0);
+    T ux, uy;
+    if (N::words_per_uniform == 1) { ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); }
+    else { ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]); }
+    const T px = N::add(static_cast<T>(i), N::sub(ux, T(0.5)));
+    const T py = N::add(static_cast<T>(j), N::sub(uy, T(0.5)));
+    Vec3<T> target;
+    target.x = N::fma(py, A.cam.dv.x, N::fma(px, A.cam.du.x, A.cam.pixel00.x));
+    target.y = N::fma(py, A.cam.dv.y, N::fma(px, A.cam.du.y, A.cam.pixel00.y));
+    target.z = N::fma(py, A.cam.dv.z, N::fma(px, A.cam.du.z, A.cam.pixel00.z));
+    Vec3<T> o = A.cam.center;
+    if (!(A.cam.defocus_angle <= T(0))) {
+        // defocus_disk_sample / random_in_unit_disk (GF camera.h:73-76, vec3.h:109-115)
+        T q0, q1;
+        for (uint32_t k = 0;; ++k) {
+            uint32_t a0, a1, b0 = 0, b1 = 0;
+            if (N::words_per_uniform == 1) {
+                if (k > 0 && (k & 1u)) ph.block((k + 1u) >> 1);
+                const bool lowpair = (k > 0) && (k & 1u);
+                a0 = lowpair ? ph.w[0] : ph.w[2];
+                a1 = lowpair ? ph.w[1] : ph.w[3];
+            } else {
+                ph.block(1u + k);
+                a0 = ph.w[0]; b0 = ph.w[1]; a1 = ph.w[2]; b1 = ph.w[3];
+            }
+            q0 = N::fma(N::uniform(a0, b0), T(2), T(-1));
+            q1 = N::fma(N::uniform(a1, b1), T(2), T(-1));
+            if (N::fma(q1, q1, N::mul(q0, q0)) < T(1)) break;
+        }
+        o.x = N::fma(q1, A.cam.disk_v.x, N::fma(q0, A.cam.disk_u.x, A.cam.center.x));
+        o.y = N::fma(q1, A.cam.disk_v.y, N::fma(q0, A.cam.disk_u.y, A.cam.center.y));
+        o.z = N::fma(q1, A.cam.disk_v.z, N::fma(q0, A.cam.disk_u.z, A.cam.center.z));
+    }
+    ps.o = o;
+    ps.d.x = N::sub(target.x, o.x); ps.d.y = N::sub(target.y, o.y); ps.d.z = N::sub(target.z, o.z);
+    ps.att.x = ps.att.y = ps.att.z = T(1);
+    const T len = N::sqrt(dot3(ps.d, ps.d));
+    ps.puy = N::mul(N::rcp(len), ps.d.y);
+}
+
+// background of the primary ray (GF camera.h:120-124): a = 0.5*(uy + 1.0) in double
+template <typename T> __device__ __forceinline__ void sky(T puy, T &r, T &g, T &b);
+template <> __device__ __forceinline__ void sky<float>(float puy, float &r, float &g, float &b) {
+    const double a = __dmul_rn(0.5, __dadd_rn((double)puy, 1.0));
+    const float t1 = __double2float_rn(__dsub_rn(1.0, a));
+    const float af = __double2float_rn(a);
+    r = __fmaf_rn(af, 0.5f, t1);
+    g = __fmaf_rn(af, 0.7f, t1);
+    b = __fadd_rn(af, t1);
+}
+template <> __device__ __forceinline__ void sky<double>(double puy, double &r, double &g, double &b) {
+    const double a = __dmul_rn(0.5, __dadd_rn(puy, 1.0));
+    const double t1 = __dsub_rn(1.0, a);
+    r = __fma_rn(a, 0.5, t1);
+    g = __fma_rn(a, 0.7, t1);
+    b = __dadd_rn(a, t1);
+}
+
+// random_unit_vector (GF vec3.h:117-127), Philox dimension depth+1, one candidate per block
+// (float) or per two blocks (double)
+template <typename T>
+__device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
+    using N = Num<T>;
+    Vec3<T> v;
+    for (uint32_t k = 0;; ++k) {
+        T ux, uy, uz;
+        if (N::words_per_uniform == 1) {
+            ph.block(k);
+            ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
+        } else {
+            ph.block(2u * k);
+            ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
+            ph.block(2u * k + 1u);
+            uz = N::uniform(ph.w[0], ph.w[1]);
+        }
+        v.x = N::fma(ux, T(2), T(-1)); v.y = N::fma(uy, T(2), T(-1)); v.z = N::fma(uz, T(2), T(-1));
+        const T l2 = dot3(v, v);
+        if (N::unit_min() < l2 && l2 <= T(1)) {
+            const T inv = N::rcp(N::sqrt(l2));
+            v.x = N::mul(inv, v.x); v.y = N::mul(inv, v.y); v.z = N::mul(inv, v.z);
+            return v;
+        }
+    }
+}
+
+// One bounce: hit record (GF hittable.h:58-63) + the material switch of GF camera.h:92-108.
+// Returns false when the path is absorbed (metal scattered below the surface, GF material.h:58).
+template <typename T>
+__device__ __forceinline__ bool scatter(const TraceArgs<T> &A, const SceneView<T> &sc, const Hit<T> &hit,
+                                        uint32_t pixel, uint32_t sample, int depth, PathState<T> &ps) {
+    using N = Num<T>;
+    const typename N::vec4 s = sc.geom[hit.id];
+    const typename N::vec4 m = sc.matl[hit.id];
+    const int type = sc.type[hit.id];
+    const Vec3<T> o = ps.o, d = ps.d;
+    Vec3<T> p;
+    p.x = N::fma(hit.t, d.x, o.x); p.y = N::fma(hit.t, d.y, o.y); p.z = N::fma(hit.t, d.z, o.z);
+    const T inv_r = N::rcp(s.w);
+    Vec3<T> n;
+    n.x = N::mul(N::sub(p.x, s.x), inv_r); n.y = N::mul(N::sub(p.y, s.y), inv_r); n.z = N::mul(N::sub(p.z, s.z), inv_r);
+    const bool front = dot3(d, n) < T(0);
+    if (!front) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+
+    Philox ph;
+    ph.open(A.seed_lo, A.seed_hi, pixel, sample, static_cast<uint32_t>(depth + 1));
+    Vec3<T> nd;
+    if (type == RT_DIELECTRIC) {
+        // dieletric_scatter (GF material.h:68-89), reflect/refract (GF vec3.h:129-138)
+        const T ri = front ? N::rcp(m.w) : m.w;
+        const T inv = N::rcp(N::sqrt(dot3(d, d)));
+        Vec3<T> ud;
+        ud.x = N::mul(inv, d.x); ud.y = N::mul(inv, d.y); ud.z = N::mul(inv, d.z);
+        Vec3<T> nud;
+        nud.x = -ud.x; nud.y = -ud.y; nud.z = -ud.z;
+        const T cos_t = N::min(dot3(nud, n), T(1));
+        const T sin_t = N::sqrt(N::fma(-cos_t, cos_t, T(1)));
+        bool reflect = N::mul(ri, sin_t) > T(1);
+        if (!reflect) {
+            // Schlick (GF material.h:62-66); (1-cos)^5 by repeated multiplication
+            T r0 = N::div(N::sub(T(1), ri), N::add(T(1), ri));
+            r0 = N::mul(r0, r0);
+            const T x1 = N::sub(T(1), cos_t), x2 = N::mul(x1, x1), x4 = N::mul(x2, x2), x5 = N::mul(x4, x1);
+            const T refl = N::fma(N::sub(T(1), r0), x5, r0);
+            ph.block(0);
+            reflect = refl > N::uniform(ph.w[0], ph.w[1]);
+        }
+        if (reflect) {
+            const T k = N::mul(T(2), dot3(ud, n));
+            nd.x = N::fma(-k, n.x, ud.x); nd.y = N::fma(-k, n.y, ud.y); nd.z = N::fma(-k, n.z, ud.z);
+        } else {
+            Vec3<T> perp;
+            perp.x = N::mul(ri, N::fma(cos_t, n.x, ud.x));
+            perp.y = N::mul(ri, N::fma(cos_t, n.y, ud.y));
+            perp.z = N::mul(ri, N::fma(cos_t, n.z, ud.z));
+            const T k = -N::sqrt(N::abs(N::sub(T(1), dot3(perp, perp))));
+            nd.x = N::fma(k, n.x, perp.x); nd.y = N::fma(k, n.y, perp.y); nd.z = N::fma(k, n.z, perp.z);
+        }
+    } else {
+        const Vec3<T> uv = unit_vector_draw<T>(ph);
+        if (type == RT_LAMBERTIAN) {
+            // lambertian_scatter (GF material.h:38-49)
+            nd.x = N::add(n.x, uv.x); nd.y = N::add(n.y, uv.y); nd.z = N::add(n.z, uv.z);
+            if (N::abs(nd.x) < N::near_zero() && N::abs(nd.y) < N::near_zero() && N::abs(nd.z) < N::near_zero()) nd = n;
+        } else {
+            // metal_scatter (GF material.h:51-59)
+            const T k = N::mul(T(2), dot3(d, n));
+            Vec3<T> rf;
+            rf.x = N::fma(-k, n.x, d.x); rf.y = N::fma(-k, n.y, d.y); rf.z = N::fma(-k, n.z, d.z);
+            const T inv = N::rcp(N::sqrt(dot3(rf, rf)));
+            nd.x = N::fma(m.w, uv.x, N::mul(inv, rf.x));
+            nd.y = N::fma(m.w, uv.y, N::mul(inv, rf.y));
+            nd.z = N::fma(m.w, uv.z, N::mul(inv, rf.z));
+            if (!(dot3(nd, n) > T(0))) return false;
+        }
+        ps.att.x = N::mul(ps.att.x, m.x); ps.att.y = N::mul(ps.att.y, m.y); ps.att.z = N::mul(ps.att.z, m.z);
+    }
+    ps.o = p;
+    ps.d = nd;
+    return true;
+}
+
+template <typename T>
+__device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) {
+    if (A.world == 1) return local_row;
+    const int tile = local_row / A.tile_rows, within = local_row - tile * A.tile_rows;
+    return (tile * A.world + A.rank) * A.tile_rows + within;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TRACE_BLOCK) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
+    using N = Num<T>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
+    const SceneView<T> sc = view_of<T>(smem, A.scene);
+    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
+
+    const int lane = threadIdx.x & 31;
+    enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
+    int state = NEED_JOB;
+    bool fresh = false;                 // next loop turn starts a new sample
+    PathState<T> ps;
+    ps.o = A.cam.center;
+    ps.d.x = T(0); ps.d.y = T(1); ps.d.z = T(0);
+    ps.att.x = ps.att.y = ps.att.z = T(1);
+    ps.puy = T(0);
+    T acc_r = T(0), acc_g = T(0), acc_b = T(0);
+    int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
+    uint32_t pixel = 0;
+    unsigned long long job = 0;
+    unsigned int n_seg = 0, n_path = 0;
+
+    for (;;) {
+        // ---- job fetch: one atomic per warp for all lanes that ran out of work ----
+        const unsigned want = __ballot_sync(FULL, state == NEED_JOB);
+        if (want) {
+            const int leader = __ffs(want) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
+            base = __shfl_sync(FULL, base, leader);
+            if (state == NEED_JOB) {
+                job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                if (job < A.total_jobs) {
+                    const unsigned long long cl = job / A.pix_local;
+                    const unsigned long long lp = job - cl * A.pix_local;
+                    const int c = A.c_begin + (int)cl;
+                    const int lr = (int)(lp / (unsigned long long)A.width);
+                    pi = (int)(lp - (unsigned long long)lr * A.width);
+                    pj = global_row(A, lr);
+                    pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
+                    sample = (int)((long long)c * A.spp / A.chunks);
+                    sample_end = (int)((long long)(c + 1) * A.spp / A.chunks);
+                    acc_r = acc_g = acc_b = T(0);
+                    state = ACTIVE;
+                    fresh = true;
+                } else {
+                    state = DEAD;
+                }
+            }
+        }
+        if (__all_sync(FULL, state == DEAD)) break;
+
+        // ---- path regeneration: a finished lane starts its next sample in place ----
+        if (state == ACTIVE && fresh) {
+            camera_ray(A, pi, pj, pixel, (uint32_t)sample, ps);
+            depth = 0;
+            fresh = false;
+        }
+
+        // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
+        const Hit<T> hit = closest_hit(sc, ps.o, ps.d, cand, TRACE_BLOCK);
+
+        // ---- shade ----
+        if (state == ACTIVE) {
+            ++n_seg;
+            bool done;
+            T cr = T(0), cg = T(0), cb = T(0);
+            if (hit.id < 0) {
+                T sr, sg, sb;
+                sky<T>(ps.puy, sr, sg, sb);
+                cr = N::mul(ps.att.x, sr); cg = N::mul(ps.att.y, sg); cb = N::mul(ps.att.z, sb);
+                done = true;
+            } else {
+                done = !scatter(A, sc, hit, pixel, (uint32_t)sample, depth, ps);
+                if (!done && ++depth >= A.max_depth) done = true;       // GF camera.h:84,127
+            }
+            if (done) {
+                acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);   // GF camera.h:160
+                ++n_path;
+                if (++sample == sample_end) {
+                    typename N::vec4 v;
+                    v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
+                    A.partial[job] = v;
+                    state = NEED_JOB;
+                } else {
+                    fresh = true;
+                }
+            }
+        }
+    }
+
+    // ---- work counters (for the roofline: segments x slots x 18 FLOP) ----
+    unsigned long long seg = n_seg, pth = n_path;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        seg += __shfl_xor_sync(FULL, seg, off);
+        pth += __shfl_xor_sync(FULL, pth, off);
+    }
+    if (lane == 0) {
+        atomicAdd(A.queue + 1, seg);
+        atomicAdd(A.queue + 2, pth);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// out[p] = gamma(scale * sum_c partial[c][p]); 4 pixels per thread, 16-byte stores.
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_kernel(const typename Num<T>::vec4 *__restrict__ partial, int chunks,
+                                                       unsigned long long pix, T scale, T *__restrict__ out) {
+    using N = Num<T>;
+    const unsigned long long quad = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long p0 = quad * 4ull;
+    if (p0 >= pix) return;
+    T v[12];
+    const int cnt = (pix - p0) < 4ull ? (int)(pix - p0) : 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        T r = T(0), g = T(0), b = T(0);
+        if (k < cnt) {
+            for (int c = 0; c < chunks; ++c) {
+                const typename N::vec4 q = partial[(unsigned long long)c * pix + p0 + k];
+                r = N::add(r, q.x); g = N::add(g, q.y); b = N::add(b, q.z);
+            }
+            r = N::mul(r, scale); g = N::mul(g, scale); b = N::mul(b, scale);          // GF camera.h:167
+            r = r > T(0) ? N::sqrt(r) : T(0);                                          // GF color.h:10-13
+            g = g > T(0) ? N::sqrt(g) : T(0);
+            b = b > T(0) ? N::sqrt(b) : T(0);
+        }
+        v[3 * k] = r; v[3 * k + 1] = g; v[3 * k + 2] = b;
+    }
+    T *dst = out + p0 * 3ull;
+    if (cnt == 4 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        constexpr int per = 16 / sizeof(T);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(v);
+#pragma unroll
+        for (int k = 0; k < 12 / per; ++k) d4[k] = s4[k];
+    } else {
+        for (int k = 0; k < 3 * cnt; ++k) dst[k] = v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_constant__ DevCamera<T> cam,
+                                                              const __grid_constant__ SceneBlob scene, int width,
+                                                              int height, int *__restrict__ ids, T *__restrict__ ts) {
+    using N = Num<T>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    stage_scene(smem, scene.base, scene.bytes, &bar);
+    const SceneView<T> sc = view_of<T>(smem, scene);
+    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
+    const long long npix = (long long)width * height;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(k / width), i = (int)(k - (long long)j * width);
+        const T fi = static_cast<T>(i), fj = static_cast<T>(j);
+        Vec3<T> d;
+        d.x = N::sub(N::fma(fj, cam.dv.x, N::fma(fi, cam.du.x, cam.pixel00.x)), cam.center.x);
+        d.y = N::sub(N::fma(fj, cam.dv.y, N::fma(fi, cam.du.y, cam.pixel00.y)), cam.center.y);
+        d.z = N::sub(N::fma(fj, cam.dv.z, N::fma(fi, cam.du.z, cam.pixel00.z)), cam.center.z);
+        const Hit<T> hit = closest_hit(sc, cam.center, d, cand, TRACE_BLOCK);
+        ids[k] = hit.id;
+        ts[k] = hit.t;
+    }
+}
+
+}  // namespace rt
+
+// ==============================================================================================
+// C ABI, device half
+// ==============================================================================================
+using namespace rt;
+
+struct rt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // scene
+    void *scene_dev = nullptr;
+    SceneBlob blob{};
+    int scene_prec = 0;                 // 0 none, 4 float, 8 double
+    // scratch
+    void *partial = nullptr;
+    size_t partial_bytes = 0;
+    void *frame = nullptr;              // device frame when the caller's buffer is host memory
+    size_t frame_bytes = 0;
+    unsigned long long *queue = nullptr;   // 4 x u64
+    rt_stats stats{};
+};
+
+#define RT_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t err__ = (call);                           \
+        if (err__ != cudaSuccess) return (int)err__;          \
+    } while (0)
+
+namespace {
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure(void **buf, size_t *have, size_t need) {
+    if (*have >= need) return 0;
+    if (*buf) { cudaError_t e = cudaFree(*buf); *buf = nullptr; *have = 0; if (e != cudaSuccess) return (int)e; }
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e != cudaSuccess) return (int)e;
+    *have = need;
+    return 0;
+}
+
+template <typename T, typename Cam> DevCamera<T> to_dev(const Cam &c) {
+    DevCamera<T> d;
+    d.center = {c.center[0], c.center[1], c.center[2]};
+    d.pixel00 = {c.pixel00[0], c.pixel00[1], c.pixel00[2]};
+    d.du = {c.du[0], c.du[1], c.du[2]};
+    d.dv = {c.dv[0], c.dv[1], c.dv[2]};
+    d.disk_u = {c.disk_u[0], c.disk_u[1], c.disk_u[2]};
+    d.disk_v = {c.disk_v[0], c.disk_v[1], c.disk_v[2]};
+    d.defocus_angle = c.defocus_angle;
+    d.scale = c.scale;
+    return d;
+}
+
+template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, int n) {
+    using V4 = typename Num<T>::vec4;
+    if (!ctx || !slots || n <= 0 || n > 65535) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const size_t n_pad = (size_t)n;                                      // vec4 arrays are 16-byte multiples already
+    const size_t type_bytes = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
+    const size_t geom_bytes = n_pad * sizeof(V4);
+    const size_t total = 2 * geom_bytes + type_bytes;
+    std::vector<unsigned char> host(total, 0);
+    V4 *geom = reinterpret_cast<V4 *>(host.data());
+    V4 *matl = reinterpret_cast<V4 *>(host.data() + geom_bytes);
+    int *type = reinterpret_cast<int *>(host.data() + 2 * geom_bytes);
+    for (int i = 0; i < n; ++i) {
+        const Slot &s = slots[i];
+        if (s.type < 0 || s.type > 2) return RT_EINVAL;
+        geom[i].x = s.cx; geom[i].y = s.cy; geom[i].z = s.cz; geom[i].w = s.r;
+        matl[i].x = s.albedo[0]; matl[i].y = s.albedo[1]; matl[i].z = s.albedo[2];
+        matl[i].w = s.type == RT_METAL ? s.fuzz : (s.type == RT_DIELECTRIC ? s.ri : T(0));
+        type[i] = s.type;
+    }
+    if (ctx->scene_dev) { RT_CUDA(cudaFree(ctx->scene_dev)); ctx->scene_dev = nullptr; }
+    RT_CUDA(cudaMalloc(&ctx->scene_dev, total));
+    RT_CUDA(cudaMemcpyAsync(ctx->scene_dev, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->blob.base = ctx->scene_dev;
+    ctx->blob.bytes = (uint32_t)total;
+    ctx->blob.matl_off = (uint32_t)geom_bytes;
+    ctx->blob.type_off = (uint32_t)(2 * geom_bytes);
+    ctx->blob.n = n;
+    ctx->scene_prec = (int)sizeof(T);
+    return RT_OK;
+}
+
+size_t trace_smem(const SceneBlob &b) { return (size_t)b.bytes + (size_t)CAND_CAP * TRACE_BLOCK * sizeof(unsigned short); }
+
+template <typename T> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
+    RT_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<T>, TRACE_BLOCK, smem));
+    if (per_sm < 1) return RT_EINVAL;
+    *grid = ctx->sm_count * per_sm;
+    cudaFuncAttributes fa;
+    RT_CUDA(cudaFuncGetAttributes(&fa, trace_kernel<T>));
+    ctx->stats.regs = fa.numRegs;
+    ctx->stats.smem_bytes = (int)(smem + fa.sharedSizeBytes);
+    ctx->stats.grid = *grid;
+    ctx->stats.block = TRACE_BLOCK;
+    return RT_OK;
+}
+
+// Launches the path tracer for chunks [c0,c1) over `rows_local` rows into `partial`.
+template <typename T, typename Cam>
+int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
+          typename Num<T>::vec4 *partial) {
+    const size_t smem = trace_smem(ctx->blob);
+    if (smem > 227 * 1024) return RT_EINVAL;          // scene too large for the shared-memory scan
+    int grid = 0;
+    int rc = launch_shape<T>(ctx, smem, &grid);
+    if (rc) return rc;
+    TraceArgs<T> A;
+    A.cam = to_dev<T>(cam);
+    A.scene = ctx->blob;
+    A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
+    A.spp = cam.spp; A.max_depth = cam.max_depth;
+    A.width = cam.width;
+    A.tile_rows = o.tile_rows; A.rank = o.rank;
+    A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
+    A.chunks = chunks; A.c_begin = c0;
+    A.pix_local = (unsigned long long)rows_local * cam.width;
+    A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
+    A.partial = partial;
+    A.queue = ctx->queue;
+    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (A.total_jobs == 0) return RT_OK;
+    const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
+    if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
+    ctx->stats.grid = grid;
+    trace_kernel<T><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    RT_CUDA(cudaGetLastError());
+    ctx->stats.launches += 1;
+    return RT_OK;
+}
+
+template <typename T>
+int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsigned long long pix, T scale, T *out_dev) {
+    if (pix == 0) return RT_OK;
+    const unsigned long long quads = (pix + 3) / 4;
+    const unsigned grid = (unsigned)((quads + 255) / 256);
+    finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(partial, chunks, pix, scale, out_dev);
+    RT_CUDA(cudaGetLastError());
+    ctx->stats.launches += 1;
+    return RT_OK;
+}
+
+int check_opts(const rt_opts &o) {
+    if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return RT_EINVAL;
+    if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
+    if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
+    if (o.accel != RT_ACCEL_LINEAR) return RT_EINVAL;
+    return RT_OK;
+}
+
+int read_counters(rt_ctx *ctx, float ms_total, float ms_trace, int chunks) {
+    unsigned long long h[4];
+    RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.segments = h[1];
+    ctx->stats.paths = h[2];
+    ctx->stats.sphere_tests = h[1] * (unsigned long long)ctx->blob.n;
+    ctx->stats.node_visits = 0;
+    ctx->stats.render_ms = ms_total;
+    ctx->stats.trace_ms = ms_trace;
+    ctx->stats.chunks = chunks;
+    return RT_OK;
+}
+
+template <typename T, typename Cam>
+int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb, float *render_ms) {
+    using V4 = typename Num<T>::vec4;
+    if (!ctx || !cam || !out_rgb) return RT_EINVAL;
+    if (!ctx->scene_dev) return RT_ENOSCENE;
+    if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
+    if (cam->width <= 0 || cam->height <= 0 || cam->spp <= 0) return RT_EINVAL;
+    rt_opts o;
+    if (opts_in) o = *opts_in; else rt_opts_default(&o);
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (o.split == RT_SPLIT_SPP) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+
+    const int rows_local = (o.split == RT_SPLIT_ROWS)
+                               ? rt_partition_rows(cam->height, o.tile_rows, o.rank, o.world, nullptr, 0)
+                               : cam->height;
+    const unsigned long long pix = (unsigned long long)rows_local * cam->width;
+    const int chunks = rt_num_chunks(cam->width, cam->height, cam->spp);
+    ctx->stats = rt_stats{};
+    const size_t out_bytes = (size_t)pix * 3 * sizeof(T);
+    const bool out_on_device = is_device_ptr(out_rgb);
+    T *frame = out_rgb;
+    if (!out_on_device) {
+        rc = ensure(&ctx->frame, &ctx->frame_bytes, out_bytes ? out_bytes : 16);
+        if (rc) return rc;
+        frame = static_cast<T *>(ctx->frame);
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (cam->max_depth <= 0) {
+        // GF camera.h:84,127: no bounce budget -> every path is black
+        RT_CUDA(cudaMemsetAsync(frame, 0, out_bytes, ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    } else {
+        rc = ensure(&ctx->partial, &ctx->partial_bytes, (size_t)pix * chunks * sizeof(V4) + 16);
+        if (rc) return rc;
+        rc = trace<T>(ctx, *cam, o, rows_local, chunks, 0, chunks, static_cast<V4 *>(ctx->partial));
+        if (rc) return rc;
+        RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        rc = finalize<T>(ctx, static_cast<const V4 *>(ctx->partial), chunks, pix, static_cast<T>(cam->scale), frame);
+        if (rc) return rc;
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (!out_on_device && out_bytes)
+        RT_CUDA(cudaMemcpyAsync(out_rgb, frame, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaEventSynchronize(ctx->ev[2]));
+    float ms_total = 0.f, ms_trace = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[2]));
+    RT_CUDA(cudaEventElapsedTime(&ms_trace, ctx->ev[0], ctx->ev[1]));
+    rc = read_counters(ctx, ms_total, ms_trace, chunks);
+    if (rc) return rc;
+    if (render_ms) *render_ms = ms_total;
+    return RT_OK;
+}
+
+template <typename T, typename Cam>
+int primary_impl(rt_ctx *ctx, const Cam *cam, int32_t *ids, T *t) {
+    if (!ctx || !cam || !ids || !t) return RT_EINVAL;
+    if (!ctx->scene_dev) return RT_ENOSCENE;
+    if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)cam->width * cam->height;
+    const bool ids_dev = is_device_ptr(ids), t_dev = is_device_ptr(t);
+    int32_t *d_ids = ids;
+    T *d_t = t;
+    void *tmp = nullptr;
+    if (!ids_dev || !t_dev) {
+        RT_CUDA(cudaMalloc(&tmp, npix * (sizeof(int32_t) + sizeof(T)) + 16));
+        if (!t_dev) d_t = static_cast<T *>(tmp);
+        if (!ids_dev) d_ids = reinterpret_cast<int32_t *>(static_cast<char *>(tmp) + npix * sizeof(T));
+    }
+    const size_t smem = trace_smem(ctx->blob);
+    int rc = RT_OK;
+    cudaError_t e = cudaFuncSetAttribute(primary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        const int grid = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        primary_kernel<T><<<grid < ctx->sm_count * 8 ? grid : ctx->sm_count * 8, TRACE_BLOCK, smem, ctx->stream>>>(
+            to_dev<T>(*cam), ctx->blob, cam->width, cam->height, d_ids, d_t);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && !ids_dev)
+        e = cudaMemcpyAsync(ids, d_ids, npix * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && !t_dev) e = cudaMemcpyAsync(t, d_t, npix * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = (int)e;
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_create(int device, rt_ctx **out) {
+    if (!out) return RT_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return RT_ENODEVICE; }
+    if (device < 0 || device >= count) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return RT_ENODEVICE;                 // sm_100a SASS only: no fallback path
+    rt_ctx *ctx = new (std::nothrow) rt_ctx;
+    if (!ctx) return RT_ENOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    ctx->own_stream = (e == cudaSuccess);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->queue), 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { rt_destroy(ctx); return (int)e; }
+    *out = ctx;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx *ctx) {
+    if (!ctx) return RT_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->scene_dev) cudaFree(ctx->scene_dev);
+    if (ctx->partial) cudaFree(ctx->partial);
+    if (ctx->frame) cudaFree(ctx->frame);
+    if (ctx->queue) cudaFree(ctx->queue);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RT_OK;
+}
+
+int rt_set_stream(rt_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return RT_OK;
+}
+
+int rt_upload_scene(rt_ctx *ctx, const rt_slot *slots, int n) { return upload<float>(ctx, slots, n); }
+int rt_upload_scene64(rt_ctx *ctx, const rt_slot64 *slots, int n) { return upload<double>(ctx, slots, n); }
+
+int rt_render(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, float *out_rgb, float *render_ms) {
+    return render_impl<float>(ctx, cam, opts, out_rgb, render_ms);
+}
+int rt_render64(rt_ctx *ctx, const rt_camera64 *cam, const rt_opts *opts, double *out_rgb, float *render_ms) {
+    return render_impl<double>(ctx, cam, opts, out_rgb, render_ms);
+}
+
+int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts_in, float *partials_dev, float *render_ms) {
+    if (!ctx || !cam || !partials_dev) return RT_EINVAL;
+    if (!ctx->scene_dev) return RT_ENOSCENE;
+    if (ctx->scene_prec != 4) return RT_EPRECISION;
+    if (cam->width <= 0 || cam->height <= 0 || cam->spp <= 0 || cam->max_depth <= 0) return RT_EINVAL;
+    rt_opts o;
+    if (opts_in) o = *opts_in; else rt_opts_default(&o);
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (!is_device_ptr(partials_dev)) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const int chunks = rt_num_chunks(cam->width, cam->height, cam->spp);
+    int32_t c0 = 0, c1 = chunks;
+    if (o.split == RT_SPLIT_SPP) { rc = rt_partition_chunks(chunks, o.rank, o.world, &c0, &c1); if (rc) return rc; }
+    else if (o.split == RT_SPLIT_ROWS) return RT_EINVAL;
+    ctx->stats = rt_stats{};
+    RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = trace<float>(ctx, *cam, o, cam->height, chunks, c0, c1, reinterpret_cast<float4 *>(partials_dev));
+    if (rc) return rc;
+    RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    RT_CUDA(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    rc = read_counters(ctx, ms, ms, chunks);
+    if (rc) return rc;
+    if (render_ms) *render_ms = ms;
+    return RT_OK;
+}
+
+int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, int chunks, float *out_rgb, float *finalize_ms) {
+    if (!ctx || !cam || !partials_dev || !out_rgb || chunks < 1) return RT_EINVAL;
+    if (!is_device_ptr(partials_dev)) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    const unsigned long long pix = (unsigned long long)cam->width * cam->height;
+    const size_t out_bytes = (size_t)pix * 3 * sizeof(float);
+    const bool out_on_device = is_device_ptr(out_rgb);
+    float *frame = out_rgb;
+    if (!out_on_device) {
+        int rc = ensure(&ctx->frame, &ctx->frame_bytes, out_bytes);
+        if (rc) return rc;
+        frame = static_cast<float *>(ctx->frame);
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = finalize<float>(ctx, reinterpret_cast<const float4 *>(partials_dev), chunks, pix, cam->scale, frame);
+    if (rc) return rc;
+    RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!out_on_device) RT_CUDA(cudaMemcpyAsync(out_rgb, frame, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    if (finalize_ms) *finalize_ms = ms;
+    return RT_OK;
+}
+
+int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t) { return primary_impl<float>(ctx, cam, ids, t); }
+int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t) { return primary_impl<double>(ctx, cam, ids, t); }
+
+int rt_get_stats(rt_ctx *ctx, rt_stats *stats) {
+    if (!ctx || !stats) return RT_EINVAL;
+    *stats = ctx->stats;
+    return RT_OK;
+}
+
+}  // extern "C"

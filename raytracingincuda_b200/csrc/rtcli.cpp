@@ -1,0 +1,242 @@
+// rtcli.cpp -- `b200-raytrace`: drop-in for the reference's global/const/tex command-line
+// renderers (GF main.cu:37-403) on top of the C ABI of include/rt_b200.h.
+//
+// Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
+// setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
+// (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
+// (--seed, --precision, --gpus, --split, --prefix, --no-ppm, --stats) defaults to the reference's
+// behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
+// (global_float_benchmark.sh:53-74) stays valid.
+#include "rt_b200.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// The text cxxopts 3.2.1 prints for the reference's option set (GF main.cu:39-55).
+const char *kUsage =
+    "Super Raytrace: Raytracing with CUDA\n"
+    "Usage:\n"
+    "  ./cuda-raytrace [OPTION...]\n"
+    "\n"
+    "      --scene_id arg  ID of the scene to render\n"
+    "      --width arg     Width of the output image (default: 320)\n"
+    "      --height arg    Height of the output image (default: 192)\n"
+    "      --samples arg   Number of samples per pixel (default: 10)\n"
+    "      --bounces arg   Maximum number of ray bounces (default: 25)\n"
+    "      --threads arg   Number of threads per 2-D thread block row. (default: \n"
+    "                      8)\n"
+    "  -h, --help          Print usage\n";
+
+// cxxopts lets exceptions escape main(): the process aborts with status 134.  Reproduce both
+// the message and the status.
+[[noreturn]] void die_like_cxxopts(const char *type, const std::string &what) {
+    std::fprintf(stderr, "terminate called after throwing an instance of 'cxxopts::exceptions::%s'\n  what():  %s\n",
+                 type, what.c_str());
+    std::abort();
+}
+
+struct Args {
+    bool help = false, have_scene = false;
+    int scene_id = 0, width = 320, height = 192, samples = 10, bounces = 25, threads = 8;
+    // extensions
+    unsigned long long seed = 1227;
+    bool use_double = false, no_ppm = false, stats = false;
+    int gpus = 1;
+    std::string split = "rows", prefix;
+};
+
+int to_int(const std::string &name, const std::string &text) {
+    char *end = nullptr;
+    const long v = std::strtol(text.c_str(), &end, 10);
+    if (text.empty() || *end != '\0')
+        die_like_cxxopts("incorrect_argument_type", "Argument '" + text + "' failed to parse");
+    (void)name;
+    return static_cast<int>(v);
+}
+
+Args parse(int argc, char **argv) {
+    Args a;
+    for (int k = 1; k < argc; ++k) {
+        std::string tok = argv[k];
+        if (tok == "-h" || tok == "--help") { a.help = true; continue; }
+        if (tok.rfind("--", 0) != 0) {
+            if (tok.size() > 1 && tok[0] == '-') die_like_cxxopts("no_such_option", "Option '" + tok.substr(1) + "' does not exist");
+            continue;   // cxxopts ignores stray positionals for this option set
+        }
+        std::string name = tok.substr(2), value;
+        bool has_value = false;
+        const size_t eq = name.find('=');
+        if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
+        const bool flag_only = (name == "no-ppm" || name == "stats");
+        static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats"};
+        bool ok = false;
+        for (const char *n : known) ok = ok || name == n;
+        if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
+        if (!flag_only && !has_value) {
+            if (k + 1 >= argc) die_like_cxxopts("missing_argument", "Option '" + name + "' is missing an argument");
+            value = argv[++k];
+        }
+        if (name == "scene_id") { a.scene_id = to_int(name, value); a.have_scene = true; }
+        else if (name == "width") a.width = to_int(name, value);
+        else if (name == "height") a.height = to_int(name, value);
+        else if (name == "samples") a.samples = to_int(name, value);
+        else if (name == "bounces") a.bounces = to_int(name, value);
+        else if (name == "threads") a.threads = to_int(name, value);
+        else if (name == "seed") a.seed = std::strtoull(value.c_str(), nullptr, 10);
+        else if (name == "precision") a.use_double = (value == "double");
+        else if (name == "gpus") a.gpus = to_int(name, value);
+        else if (name == "split") a.split = value;
+        else if (name == "prefix") a.prefix = value;
+        else if (name == "no-ppm") a.no_ppm = true;
+        else if (name == "stats") a.stats = true;
+    }
+    return a;
+}
+
+// The reference's CUDA_SAFE_CALL (GF main.cu:14-21): message on stderr, exit with the code.
+void check(int rc, const char *what, int line) {
+    if (rc == RT_OK) return;
+    std::fprintf(stderr, "CUDA_SAFE_CALL: %s (%s) %s %d\n", rt_error_string(rc), what, __FILE__, line);
+    std::exit(rc > 0 ? rc : 1);
+}
+#define CHECK(call) check((call), #call, __LINE__)
+
+struct Device {
+    rt_ctx *ctx = nullptr;
+    rt_stats stats{};
+    float render_ms = 0.f;
+    std::vector<int32_t> rows;
+    std::vector<float> rgb;
+    std::vector<double> rgb64;
+};
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    const Args a = parse(argc, argv);
+    if (a.help) { std::cout << kUsage << "\n"; return 0; }
+    if (!a.have_scene) {
+        std::cerr << "Error: --scene_id is required." << "\n";
+        std::cout << kUsage << "\n";
+        return 1;
+    }
+    if (a.width <= 0 || a.height <= 0 || a.samples <= 0 || a.gpus < 1) {
+        std::cerr << "Error: --width/--height/--samples/--gpus must be positive." << "\n";
+        return 1;
+    }
+
+    // contexts first: like the reference, context creation is outside the end-to-end timer
+    // (GF main.cu:81-95)
+    std::vector<Device> dev(static_cast<size_t>(a.gpus));
+    for (int g = 0; g < a.gpus; ++g) CHECK(rt_create(g, &dev[g].ctx));
+    const auto e2e_start = std::chrono::steady_clock::now();
+
+    const int W = a.width, H = a.height;
+    const size_t npix = static_cast<size_t>(W) * H;
+    std::vector<float> frame;
+    std::vector<double> frame64;
+
+    // scene (GF main.cu:142-321)
+    std::vector<rt_slot> slots;
+    std::vector<rt_slot64> slots64;
+    int n = 0;
+    if (a.use_double) {
+        n = rt_scene_generate64(a.scene_id, nullptr, 0);
+        slots64.resize(static_cast<size_t>(n));
+        rt_scene_generate64(a.scene_id, slots64.data(), n);
+        for (auto &d : dev) CHECK(rt_upload_scene64(d.ctx, slots64.data(), n));
+        frame64.resize(npix * 3);
+    } else {
+        n = rt_scene_generate(a.scene_id, nullptr, 0);
+        slots.resize(static_cast<size_t>(n));
+        rt_scene_generate(a.scene_id, slots.data(), n);
+        for (auto &d : dev) CHECK(rt_upload_scene(d.ctx, slots.data(), n));
+        frame.resize(npix * 3);
+    }
+
+    rt_camera cam;
+    rt_camera64 cam64;
+    CHECK(rt_camera_init(&cam, W, H, a.samples, a.bounces));
+    CHECK(rt_camera_init64(&cam64, W, H, a.samples, a.bounces));
+
+    // render (GF main.cu:326-341): one host thread per device, interleaved row tiles
+    std::vector<std::thread> workers;
+    std::vector<int> rcs(static_cast<size_t>(a.gpus), RT_OK);
+    for (int g = 0; g < a.gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            Device &d = dev[g];
+            rt_opts o;
+            rt_opts_default(&o);
+            o.seed = a.seed;
+            o.threads = a.threads;
+            if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; }
+            const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
+            d.rows.resize(static_cast<size_t>(nrows));
+            if (a.gpus > 1) rt_partition_rows(H, o.tile_rows, g, a.gpus, d.rows.data(), nrows);
+            if (a.use_double) {
+                double *dst = a.gpus > 1 ? (d.rgb64.resize(static_cast<size_t>(nrows) * W * 3), d.rgb64.data()) : frame64.data();
+                rcs[g] = rt_render64(d.ctx, &cam64, &o, dst, &d.render_ms);
+            } else {
+                float *dst = a.gpus > 1 ? (d.rgb.resize(static_cast<size_t>(nrows) * W * 3), d.rgb.data()) : frame.data();
+                rcs[g] = rt_render(d.ctx, &cam, &o, dst, &d.render_ms);
+            }
+            rt_get_stats(d.ctx, &d.stats);
+        });
+    }
+    for (auto &t : workers) t.join();
+    for (int g = 0; g < a.gpus; ++g) CHECK(rcs[g]);
+    float render_ms = 0.f;
+    for (const auto &d : dev) render_ms = d.render_ms > render_ms ? d.render_ms : render_ms;   // max over devices
+    if (a.gpus > 1) {
+        for (const auto &d : dev)
+            for (size_t r = 0; r < d.rows.size(); ++r) {
+                const size_t dst = static_cast<size_t>(d.rows[r]) * W * 3, src = r * W * 3;
+                if (a.use_double) std::memcpy(&frame64[dst], &d.rgb64[src], sizeof(double) * W * 3);
+                else std::memcpy(&frame[dst], &d.rgb[src], sizeof(float) * W * 3);
+            }
+    }
+    std::cout << std::fixed << std::setprecision(8) << std::setw(15) << render_ms << ",";
+
+    // PPM (GF main.cu:347-379)
+    if (!a.no_ppm) {
+        std::stringstream name;
+        name << (a.prefix.empty() ? (a.use_double ? "b200_double_" : "b200_float_") : a.prefix)
+             << "scene" << a.scene_id << "_" << W << "x" << H << "_" << a.samples << "samples"
+             << "_" << a.bounces << "bounces" << "_" << a.threads << "threadsPerBlockRow" << ".ppm";
+        const std::string path = name.str();
+        const int rc = a.use_double ? rt_ppm_write64(path.c_str(), frame64.data(), W, H)
+                                    : rt_ppm_write(path.c_str(), frame.data(), W, H);
+        if (rc != RT_OK) {
+            std::cerr << "Error: Could not open file for writing: " << path << "\n";
+            return -1;
+        }
+    }
+
+    unsigned long long segments = 0, paths = 0;
+    for (auto &d : dev) { segments += d.stats.segments; paths += d.stats.paths; }
+    const rt_stats st0 = dev[0].stats;
+    for (auto &d : dev) rt_destroy(d.ctx);
+    const auto e2e_stop = std::chrono::steady_clock::now();
+    const float e2e_ms = std::chrono::duration<float, std::milli>(e2e_stop - e2e_start).count();
+    std::cout << std::fixed << std::setprecision(8) << std::setw(15) << e2e_ms << "\n";
+
+    if (a.stats) {
+        const double mps = static_cast<double>(npix) * a.samples / (render_ms * 1e-3) / 1e6;
+        std::fprintf(stderr,
+                     "{\"mpath_samples_per_s\": %.3f, \"paths\": %llu, \"segments\": %llu, \"slots\": %d, "
+                     "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d}\n",
+                     mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks);
+    }
+    return 0;
+}

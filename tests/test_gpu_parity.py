@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+
+Bars: scene bytes, primary (slot id, t) and the rendered float image are BIT-EXACT against the
+oracle on the same seeded inputs; converged radiance is within MAE <= 1/255 per channel and
+PSNR >= 40 dB of the reference's own global-float render (BASELINE.json north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import raytracingincuda_b200 as rt
+from raytracingincuda_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def image_metrics(a, b):
+    """Per-channel MAE (code values) and PSNR (dB) between two uint8 images."""
+    d = a.astype(np.float64) - b.astype(np.float64)
+    mae = np.abs(d).mean(axis=(0, 1))
+    mse = (d ** 2).mean()
+    psnr = 10 * np.log10(255.0 ** 2 / mse) if mse > 0 else np.inf
+    return mae, psnr
+
+
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+@pytest.mark.parametrize("size", [(320, 192), (97, 61)])
+def test_primary_hits_bit_exact_vs_oracle(renderer, scene_id, size):
+    w, h = size
+    slots = rt.scene(scene_id)
+    renderer.upload_scene(slots)
+    cam = rt.camera(w, h)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(O.scene(scene_id), O.camera(w, h))
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(t), bits(ot))
+    assert (ids >= 0).any() and (ids < 0).any()
+
+
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+def test_primary_hits_bit_exact_vs_oracle_double(renderer, scene_id):
+    slots = rt.scene(scene_id, double=True)
+    renderer.upload_scene(slots)
+    cam = rt.camera(160, 96, double=True)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(O.scene(scene_id, True), O.camera(160, 96, double=True))
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(t), bits(ot))
+
+
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_primary_hits_bit_exact_vs_reference_golden(renderer, golden_dir, scene_id, tag):
+    """(slot id, t) of the reference's own hit_world(), captured on a B200 (make_goldens_gpu.py)."""
+    path = os.path.join(golden_dir, f"primary_scene{scene_id}_{tag}.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference golden not generated yet")
+    g = np.load(path)
+    h, w = g["ids"].shape
+    double = tag == "f64"
+    renderer.upload_scene(rt.scene(scene_id, double=double))
+    ids, t = renderer.primary_hits(rt.camera(w, h, double=double))
+    assert np.array_equal(ids, g["ids"].astype(np.int32))
+    assert np.array_equal(bits(t), bits(g["t"]))
+
+
+@pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 48, 32, 12, 25), (2, 64, 40, 16, 50), (3, 40, 24, 9, 50),
+                                                     (1, 33, 17, 3, 4)])
+def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth):
+    slots = rt.scene(scene_id)
+    renderer.upload_scene(slots)
+    cam = rt.camera(w, h, spp, depth)
+    img = renderer.render(cam)
+    ref, seg = O.render(O.scene(scene_id), O.camera(w, h, spp, depth))
+    st = renderer.stats()
+    assert st.paths == w * h * spp
+    assert st.segments == seg
+    mism = np.argwhere(bits(img) != bits(ref))
+    assert len(mism) == 0, f"{len(mism)} differing channels, first {mism[:3]}"
+
+
+def test_render_bit_exact_vs_oracle_double(renderer):
+    renderer.upload_scene(rt.scene(1, double=True))
+    cam = rt.camera(32, 20, 6, 25, double=True)
+    img = renderer.render(cam)
+    ref, seg = O.render(O.scene(1, True), O.camera(32, 20, 6, 25, double=True))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(img), bits(ref))
+
+
+def test_render_is_deterministic_and_seeded(renderer):
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(160, 96, 16, 25)
+    a = renderer.render(cam)
+    b = renderer.render(cam)
+    assert np.array_equal(bits(a), bits(b))
+    c = renderer.render(cam, api.make_opts(seed=99))
+    assert not np.array_equal(bits(a), bits(c))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_split_equals_whole_frame(renderer, world):
+    """Interleaved row tiles (RT_SPLIT_ROWS) reassemble to the 1-GPU image bit for bit."""
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(96, 70, 8, 25)          # 70 rows: last tile is partial
+    whole = renderer.render(cam)
+    out = np.zeros_like(whole)
+    seen = np.zeros(cam.height, dtype=int)
+    for rank in range(world):
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=8)
+        part = renderer.render(cam, o)
+        rows = rt.partition_rows(cam.height, 8, rank, world)
+        assert part.shape[0] == len(rows)
+        out[rows] = part
+        seen[rows] += 1
+    assert (seen == 1).all()
+    assert np.array_equal(bits(out), bits(whole))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_spp_split_equals_whole_frame(renderer, world):
+    """Chunk partials rendered per rank (RT_SPLIT_SPP) and summed in chunk order give the
+    1-GPU image bit for bit."""
+    import torch
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(64, 40, 40, 25)
+    whole = renderer.render(cam)
+    C = rt.num_chunks(64, 40, 40)
+    planes = torch.zeros((C, 40 * 64, 4), dtype=torch.float32, device="cuda:0")
+    for rank in range(world):
+        c0, c1 = rt.partition_chunks(C, rank, world)
+        o = api.make_opts(split=api.SPLIT_SPP, rank=rank, world=world)
+        if c1 > c0:
+            renderer.render_partials(cam, o, planes[c0:c1])
+    torch.cuda.synchronize()
+    img = renderer.finalize(cam, planes, C)
+    assert np.array_equal(bits(img), bits(whole))
+
+
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+def test_converged_radiance_vs_reference(renderer, golden_dir, scene_id):
+    """MAE <= 1/255 per channel and PSNR >= 40 dB against the reference global-float PPM
+    (rendered on a B200 by the reference binary rebuilt for sm_100), 320x192, 4096 spp, 50 bounces."""
+    path = os.path.join(golden_dir, f"ref_scene{scene_id}_f32_320x192_4096spp_50b.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference golden not generated yet")
+    ref = np.load(path)["img"]
+    renderer.upload_scene(rt.scene(scene_id))
+    cam = rt.camera(320, 192, 4096, 50)
+    a = rt.ppm_quantise(renderer.render(cam))
+    b = rt.ppm_quantise(renderer.render(cam, api.make_opts(seed=4242)))
+    mae, psnr = image_metrics(a, ref)
+    floor_mae, floor_psnr = image_metrics(a, b)       # new-vs-new two-seed noise floor
+    print(f"scene {scene_id}: vs reference MAE {mae} PSNR {psnr:.2f} dB; two-seed floor MAE {floor_mae} PSNR {floor_psnr:.2f} dB")
+    assert (mae <= 1.0).all(), (mae, floor_mae)
+    assert psnr >= 40.0, (psnr, floor_psnr)
+    # a bias would show as an error well above the noise floor
+    assert (mae <= floor_mae * 1.5 + 0.1).all(), (mae, floor_mae)
+
+
+def test_full_size_properties(renderer):
+    """BASELINE config 2 size (1920x1080), reduced spp: path count, finite non-negative output,
+    top rows are sky, image responds to the seed only in the noise."""
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(1920, 1080, 8, 25)
+    img = renderer.render(cam)
+    st = renderer.stats()
+    assert st.paths == 1920 * 1080 * 8
+    assert 1.5 < st.segments / st.paths < 4.0
+    assert np.isfinite(img).all() and (img >= 0).all() and (img <= 1.0001).all()
+    assert img[:40].mean() > 0.6                     # sky gradient
+    ids, t = renderer.primary_hits(rt.camera(1920, 1080))
+    assert (ids[0] == -1).all() and (ids[-1] >= 0).all()     # top row sky, bottom row ground or a sphere
+    assert (ids[-1] == 0).any()
+
+
+def test_zero_bounces_is_black(renderer):
+    renderer.upload_scene(rt.scene(2))
+    img = renderer.render(rt.camera(32, 16, 4, 0))
+    assert (img == 0).all()
