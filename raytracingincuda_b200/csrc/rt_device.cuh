@@ -94,9 +94,10 @@ struct Philox {
 
 // ------------------------------------------------------------------------------------------
 // Scene blob as uploaded by rt_upload_scene: one contiguous, 16-byte aligned device buffer
-//   [vec4 geom[n_pad]]   centre.xyz, radius            (the only array the scan reads)
-//   [vec4 matl[n_pad]]   albedo.xyz, param (fuzz for metal, refraction index for dielectric)
-//   [int  type[n_pad4]]
+//   [vec4 geom[n32]]     centre.xyz, radius; n32 = n rounded up to 32, padding is zero records
+//                        (the only array the scan reads)
+//   [vec4 matl[n]]       albedo.xyz, param (fuzz for metal, refraction index for dielectric)
+//   [int  type[n4]]
 // staged into shared memory by one thread with cp.async.bulk + an mbarrier (TMA bulk copy).
 template <typename T> struct SceneView {
     const typename Num<T>::vec4 *geom;
@@ -150,83 +151,145 @@ __device__ __forceinline__ void stage_scene(void *smem_dst, const void *gmem_src
             off += piece;
         }
     }
-    // every thread waits for phase 0 of the barrier
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar_a)
-            : "memory");
-    }
+    // every thread waits for phase 0 of the barrier (try_wait suspends the thread in hardware)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "RT_STAGE_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra RT_STAGE_DONE;\n\t"
+        "bra RT_STAGE_WAIT;\n\t"
+        "RT_STAGE_DONE:\n\t"
+        "}" ::"r"(bar_a)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t tail_mask_of(int n) {
+    const int rem = n - 32 * ((n + 31) / 32 - 1);            // 1..32 valid slots in the last block
+    return rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);
 }
 
 // ------------------------------------------------------------------------------------------
-// hit_world (GF hittable.h:80-98) as a two-phase scan.
-//  phase 1: for every slot, the discriminant exactly as the reference computes it; slots with
-//           disc >= 0 (0.4 % of tests) are appended to a per-thread candidate list in shared
-//           memory -- no sqrt/div and almost no divergence in the hot loop.
+// Explicit shared-space loads of one geometry record (centre.xyz, radius).  A 32-bit shared
+// address + immediate offset keeps the scan at one LDS.128 per sphere with no address math.
+template <typename T> __device__ __forceinline__ typename Num<T>::vec4 lds_geom(uint32_t addr);
+template <> __device__ __forceinline__ float4 lds_geom<float>(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ double4 lds_geom<double>(uint32_t addr) {
+    double4 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t sign_word(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__double2hiint(x); }
+
+// ------------------------------------------------------------------------------------------
+// hit_world (GF hittable.h:80-98) as a two-phase scan over geometry in shared memory.
+//  phase 1: slots are visited in blocks of 32.  Per slot: one LDS.128, the discriminant exactly
+//           as the reference computes it (12 FP32 instructions) and ONE funnel shift that
+//           collects its sign bit -- no compare, no branch.  After a block the 32 sign bits are
+//           inspected once; slots with disc >= 0 (0.4 % of tests) are appended to a per-thread
+//           candidate list in shared memory.
+//           (disc is never -0: fma(h,h,-m) of an exact cancellation rounds to +0, so "sign bit
+//           clear" is exactly the reference's !(disc < 0) for every non-NaN value; a NaN
+//           discriminant yields no hit in the reference either, GF hittable.h:49-55.)
 //  phase 2: candidates are revisited in slot order with the reference's root logic and a
-//           shrinking tmax, so the result (slot id, t) is the one the reference's loop produces:
-//           strict tmin < t < closest, lowest slot wins ties.
+//           shrinking tmax, so (slot id, t) is what the reference's loop produces: strict
+//           tmin < t < closest, lowest slot wins ties.
 // `cand` points at this thread's column of a [CAND_CAP][blockDim.x] uint16 array.
+// The geometry array is padded with zero records to a multiple of 32; `tail_mask` clears the
+// padding's bits in the last block.
 constexpr int CAND_CAP = 24;
 
 template <typename T> struct Hit { T t; int id; };
 
+struct ScanGeom {
+    uint32_t addr;        // shared-space byte address of geom[0]
+    int blocks;           // ceil(n / 32)
+    uint32_t tail_mask;   // valid-slot bits of the last block (slot k of a block <-> bit 31-k)
+};
+
 template <typename T>
-__device__ __forceinline__ void resolve_candidates(const SceneView<T> &sc, const Vec3<T> &o, const Vec3<T> &d,
-                                                   T a, const unsigned short *cand, int stride, int count,
-                                                   Hit<T> &hit) {
+__device__ __forceinline__ T disc_of(const typename Num<T>::vec4 &s, const Vec3<T> &o, const Vec3<T> &d, T a, T &h) {
     using N = Num<T>;
-    for (int k = 0; k < count; ++k) {
-        const int id = cand[k * stride];
-        const typename N::vec4 s = sc.geom[id];
-        const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
-        const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
-        const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
-        const T c = N::fma(-s.w, s.w, q);
-        const T disc = N::fma(h, h, -N::mul(a, c));
-        const T sq = N::sqrt(disc);
-        T root = N::div(N::sub(h, sq), a);
-        if (!(N::tmin() < root && root < hit.t)) {
-            root = N::div(N::add(h, sq), a);
-            if (!(N::tmin() < root && root < hit.t)) continue;
-        }
-        hit.t = root;
-        hit.id = id;
+    const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
+    h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
+    const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
+    const T c = N::fma(-s.w, s.w, q);
+    return N::fma(h, h, -N::mul(a, c));
+}
+
+// GF hittable.h:49-56 for one slot whose discriminant is >= 0: nearest root strictly inside
+// (tmin, hit.t), else the far root, else no hit.
+template <typename T>
+__device__ __forceinline__ void try_slot(uint32_t geom_addr, int id, const Vec3<T> &o, const Vec3<T> &d, T a,
+                                         T disc, T h, Hit<T> &hit) {
+    using N = Num<T>;
+    (void)geom_addr; (void)o; (void)d;
+    const T sq = N::sqrt(disc);
+    T root = N::div(N::sub(h, sq), a);
+    if (!(N::tmin() < root && root < hit.t)) {
+        root = N::div(N::add(h, sq), a);
+        if (!(N::tmin() < root && root < hit.t)) return;
     }
+    hit.t = root;
+    hit.id = id;
 }
 
 template <typename T>
-__device__ __forceinline__ Hit<T> closest_hit(const SceneView<T> &sc, const Vec3<T> &o, const Vec3<T> &d,
+__device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
                                               unsigned short *cand, int stride) {
     using N = Num<T>;
+    constexpr uint32_t REC = sizeof(typename N::vec4);
     const T a = dot3(d, d);                                     // GF hittable.h:42
+    int count = 0;
+    uint32_t addr = g.addr;
+    for (int b = 0; b < g.blocks; ++b, addr += 32u * REC) {
+        uint32_t signs = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const typename N::vec4 s = lds_geom<T>(addr + (uint32_t)k * REC);
+            T h;
+            const T disc = disc_of<T>(s, o, d, a, h);           // GF hittable.h:41-46
+            signs = __funnelshift_l(sign_word(disc), signs, 1); // signs = signs << 1 | (disc < 0)
+        }
+        uint32_t m = ~signs;
+        if (b == g.blocks - 1) m &= g.tail_mask;
+        if (m) {                                                // GF hittable.h:47, 0.4 % of tests
+            const int base = b * 32;
+            do {
+                const int k = __clz(m);
+                m &= ~(0x80000000u >> k);
+                if (count < CAND_CAP) cand[count * stride] = static_cast<unsigned short>(base + k);
+                ++count;
+            } while (m);
+        }
+    }
     Hit<T> hit;
     hit.t = N::inf();
     hit.id = -1;
-    int count = 0;
-    const int n = sc.n;
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-        const typename N::vec4 s = sc.geom[i];
-        const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
-        const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
-        const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
-        const T c = N::fma(-s.w, s.w, q);
-        const T disc = N::fma(h, h, -N::mul(a, c));
-        if (!(disc < T(0))) {                                   // GF hittable.h:47
-            cand[count * stride] = static_cast<unsigned short>(i);
-            if (++count == CAND_CAP) {
-                resolve_candidates(sc, o, d, a, cand, stride, count, hit);
-                count = 0;
-            }
+    if (count <= CAND_CAP) {
+        for (int k = 0; k < count; ++k) {
+            const int id = cand[k * stride];
+            const typename N::vec4 s = lds_geom<T>(g.addr + (uint32_t)id * REC);
+            T h;
+            const T disc = disc_of<T>(s, o, d, a, h);
+            try_slot<T>(g.addr, id, o, d, a, disc, h, hit);
+        }
+    } else {
+        // more candidate slots than the list holds (never in the reference's scenes): rescan
+        // every slot in order, exactly like the reference's loop
+        for (int id = 0; id < n; ++id) {
+            const typename N::vec4 s = lds_geom<T>(g.addr + (uint32_t)id * REC);
+            T h;
+            const T disc = disc_of<T>(s, o, d, a, h);
+            if (!(disc < T(0))) try_slot<T>(g.addr, id, o, d, a, disc, h, hit);
         }
     }
-    resolve_candidates(sc, o, d, a, cand, stride, count, hit);
     return hit;
 }
 

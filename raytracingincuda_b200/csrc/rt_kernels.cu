@@ -232,6 +232,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) trace_kernel(const __grid_constan
     stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
     const SceneView<T> sc = view_of<T>(smem, A.scene);
     unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
+    ScanGeom geo;
+    geo.addr = smem_u32(smem);
+    geo.blocks = (A.scene.n + 31) / 32;
+    geo.tail_mask = tail_mask_of(A.scene.n);
 
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) trace_kernel(const __grid_constan
         }
 
         // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
-        const Hit<T> hit = closest_hit(sc, ps.o, ps.d, cand, TRACE_BLOCK);
+        const Hit<T> hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
 
         // ---- shade ----
         if (state == ACTIVE) {
@@ -377,8 +381,11 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     stage_scene(smem, scene.base, scene.bytes, &bar);
-    const SceneView<T> sc = view_of<T>(smem, scene);
     unsigned short *cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
+    ScanGeom geo;
+    geo.addr = smem_u32(smem);
+    geo.blocks = (scene.n + 31) / 32;
+    geo.tail_mask = tail_mask_of(scene.n);
     const long long npix = (long long)width * height;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(k / width), i = (int)(k - (long long)j * width);
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
         d.x = N::sub(N::fma(fj, cam.dv.x, N::fma(fi, cam.du.x, cam.pixel00.x)), cam.center.x);
         d.y = N::sub(N::fma(fj, cam.dv.y, N::fma(fi, cam.du.y, cam.pixel00.y)), cam.center.y);
         d.z = N::sub(N::fma(fj, cam.dv.z, N::fma(fi, cam.du.z, cam.pixel00.z)), cam.center.z);
-        const Hit<T> hit = closest_hit(sc, cam.center, d, cand, TRACE_BLOCK);
+        const Hit<T> hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
         ids[k] = hit.id;
         ts[k] = hit.t;
     }
@@ -459,14 +466,15 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     using V4 = typename Num<T>::vec4;
     if (!ctx || !slots || n <= 0 || n > 65535) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
-    const size_t n_pad = (size_t)n;                                      // vec4 arrays are 16-byte multiples already
+    const size_t n32 = ((size_t)n + 31) & ~(size_t)31;                    // the scan walks blocks of 32 slots
     const size_t type_bytes = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
-    const size_t geom_bytes = n_pad * sizeof(V4);
-    const size_t total = 2 * geom_bytes + type_bytes;
+    const size_t geom_bytes = n32 * sizeof(V4);
+    const size_t matl_bytes = (size_t)n * sizeof(V4);
+    const size_t total = geom_bytes + matl_bytes + type_bytes;
     std::vector<unsigned char> host(total, 0);
     V4 *geom = reinterpret_cast<V4 *>(host.data());
     V4 *matl = reinterpret_cast<V4 *>(host.data() + geom_bytes);
-    int *type = reinterpret_cast<int *>(host.data() + 2 * geom_bytes);
+    int *type = reinterpret_cast<int *>(host.data() + geom_bytes + matl_bytes);
     for (int i = 0; i < n; ++i) {
         const Slot &s = slots[i];
         if (s.type < 0 || s.type > 2) return RT_EINVAL;
@@ -482,7 +490,7 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     ctx->blob.base = ctx->scene_dev;
     ctx->blob.bytes = (uint32_t)total;
     ctx->blob.matl_off = (uint32_t)geom_bytes;
-    ctx->blob.type_off = (uint32_t)(2 * geom_bytes);
+    ctx->blob.type_off = (uint32_t)(geom_bytes + matl_bytes);
     ctx->blob.n = n;
     ctx->scene_prec = (int)sizeof(T);
     return RT_OK;

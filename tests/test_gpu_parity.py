@@ -185,3 +185,49 @@ def test_zero_bounces_is_black(renderer):
     renderer.upload_scene(rt.scene(2))
     img = renderer.render(rt.camera(32, 16, 4, 0))
     assert (img == 0).all()
+
+
+def concentric_scene(n_shells=64):
+    """n_shells nested spheres around the look-at point: rays through the middle have far more
+    discriminant-positive slots than the per-thread candidate list holds (24), which exercises
+    the in-order rescan path; plus the reference's ground sphere and a metal and a glass shell."""
+    s = np.zeros(n_shells + 1, dtype=api.SLOT_DTYPE)
+    s["c"][0] = (0, -1000, 0)
+    s["r"][0] = 1000
+    s["albedo"][0] = 0.5
+    for k in range(n_shells):
+        s["c"][k + 1] = (0, 1, 0)
+        s["r"][k + 1] = 0.25 + 0.02 * k
+        s["type"][k + 1] = k % 3
+        s["albedo"][k + 1] = (0.9, 0.5 + 0.005 * k, 0.3)
+        s["fuzz"][k + 1] = 0.1 if k % 3 == 1 else 0
+        s["ri"][k + 1] = 1.5 if k % 3 == 2 else 0
+    return s
+
+
+def test_candidate_overflow_rescan_is_exact(renderer):
+    slots = concentric_scene()
+    renderer.upload_scene(slots)
+    cam = rt.camera(80, 48, 6, 12)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(slots, O.camera(80, 48))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+    assert (ids == len(slots) - 1).any()                 # the outermost shell is what a ray meets first
+    img = renderer.render(cam)
+    ref, seg = O.render(slots, O.camera(80, 48, 6, 12))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(img), bits(ref))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 64, 65])
+def test_slot_counts_around_block_boundaries(renderer, n):
+    """The scan walks blocks of 32 slots with a tail mask: every count around the boundaries."""
+    slots = rt.scene(1)[:n].copy()
+    renderer.upload_scene(slots)
+    cam = rt.camera(64, 40, 4, 8)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(slots, O.camera(64, 40))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+    img = renderer.render(cam)
+    ref, _ = O.render(slots, O.camera(64, 40, 4, 8))
+    assert np.array_equal(bits(img), bits(ref))
