@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+# RT_B200_LIB selects another build of the same library (kernel tuning variants); never a fallback
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
 SPLIT_NONE, SPLIT_ROWS, SPLIT_SPP = 0, 1, 2
 LAMBERTIAN, METAL, DIELECTRIC = 0, 1, 2

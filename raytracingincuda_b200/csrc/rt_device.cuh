@@ -94,7 +94,7 @@ struct Philox {
 
 // ------------------------------------------------------------------------------------------
 // Scene blob as uploaded by rt_upload_scene: one contiguous, 16-byte aligned device buffer
-//   [vec4 geom[n32]]     centre.xyz, radius; n32 = n rounded up to 32, padding is zero records
+//   [vec4 geom[n8]]      centre.xyz, radius; n8 = n rounded up to 8, padding is zero records
 //                        (the only array the scan reads)
 //   [vec4 matl[n]]       albedo.xyz, param (fuzz for metal, refraction index for dielectric)
 //   [int  type[n4]]
@@ -164,11 +164,6 @@ __device__ __forceinline__ void stage_scene(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
-__device__ __forceinline__ uint32_t tail_mask_of(int n) {
-    const int rem = n - 32 * ((n + 31) / 32 - 1);            // 1..32 valid slots in the last block
-    return rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);
-}
-
 // ------------------------------------------------------------------------------------------
 // Explicit shared-space loads of one geometry record (centre.xyz, radius).  A 32-bit shared
 // address + immediate offset keeps the scan at one LDS.128 per sphere with no address math.
@@ -201,17 +196,28 @@ __device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__dou
 //           shrinking tmax, so (slot id, t) is what the reference's loop produces: strict
 //           tmin < t < closest, lowest slot wins ties.
 // `cand` points at this thread's column of a [CAND_CAP][blockDim.x] uint16 array.
-// The geometry array is padded with zero records to a multiple of 32; `tail_mask` clears the
-// padding's bits in the last block.
+// After the full blocks a tail of up to three groups of 8 covers n % 32; the geometry array is
+// padded with zero records to a multiple of 8 and `tail_mask` clears the padding's bits.
 constexpr int CAND_CAP = 24;
 
 template <typename T> struct Hit { T t; int id; };
 
 struct ScanGeom {
     uint32_t addr;        // shared-space byte address of geom[0]
-    int blocks;           // ceil(n / 32)
-    uint32_t tail_mask;   // valid-slot bits of the last block (slot k of a block <-> bit 31-k)
+    int blocks;           // n / 32 full blocks
+    int tail_groups;      // ceil((n % 32) / 8) groups of 8 after the full blocks
+    uint32_t tail_mask;   // valid-slot bits of the tail word (slot k of a word <-> bit 31-k)
 };
+
+__device__ __forceinline__ ScanGeom scan_geom(uint32_t addr, int n) {
+    ScanGeom g;
+    g.addr = addr;
+    g.blocks = n >> 5;
+    const int rem = n & 31;
+    g.tail_groups = (rem + 7) >> 3;
+    g.tail_mask = rem ? ~(0xffffffffu >> rem) : 0u;
+    return g;
+}
 
 template <typename T>
 __device__ __forceinline__ T disc_of(const typename Num<T>::vec4 &s, const Vec3<T> &o, const Vec3<T> &d, T a, T &h) {
@@ -240,6 +246,20 @@ __device__ __forceinline__ void try_slot(uint32_t geom_addr, int id, const Vec3<
     hit.id = id;
 }
 
+// Appends the slots flagged in `m` (slot k of the word <-> bit 31-k) to the candidate list.
+__device__ __forceinline__ void push_candidates(uint32_t m, int base, unsigned short *cand, int stride, int &count) {
+    do {
+        const int k = __clz(m);
+        m &= ~(0x80000000u >> k);
+        if (count < CAND_CAP) cand[count * stride] = static_cast<unsigned short>(base + k);
+        ++count;
+    } while (m);
+}
+
+#ifndef RT_SCAN_UNROLL
+#define RT_SCAN_UNROLL 16          // slots per unrolled body; 32 / RT_SCAN_UNROLL bodies per sign word
+#endif
+
 template <typename T>
 __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
                                               unsigned short *cand, int stride) {
@@ -248,26 +268,37 @@ __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Ve
     const T a = dot3(d, d);                                     // GF hittable.h:42
     int count = 0;
     uint32_t addr = g.addr;
-    for (int b = 0; b < g.blocks; ++b, addr += 32u * REC) {
+    // full blocks of 32 slots: one sign word each
+    for (int b = 0; b < g.blocks; ++b) {
         uint32_t signs = 0;
+#pragma unroll 1
+        for (int part = 0; part < 32 / RT_SCAN_UNROLL; ++part, addr += RT_SCAN_UNROLL * REC) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const typename N::vec4 s = lds_geom<T>(addr + (uint32_t)k * REC);
-            T h;
-            const T disc = disc_of<T>(s, o, d, a, h);           // GF hittable.h:41-46
-            signs = __funnelshift_l(sign_word(disc), signs, 1); // signs = signs << 1 | (disc < 0)
+            for (int k = 0; k < RT_SCAN_UNROLL; ++k) {
+                const typename N::vec4 s = lds_geom<T>(addr + (uint32_t)k * REC);
+                T h;
+                const T disc = disc_of<T>(s, o, d, a, h);           // GF hittable.h:41-46
+                signs = __funnelshift_l(sign_word(disc), signs, 1); // signs = signs << 1 | (disc < 0)
+            }
         }
-        uint32_t m = ~signs;
-        if (b == g.blocks - 1) m &= g.tail_mask;
-        if (m) {                                                // GF hittable.h:47, 0.4 % of tests
-            const int base = b * 32;
-            do {
-                const int k = __clz(m);
-                m &= ~(0x80000000u >> k);
-                if (count < CAND_CAP) cand[count * stride] = static_cast<unsigned short>(base + k);
-                ++count;
-            } while (m);
+        const uint32_t m = ~signs;
+        if (m) push_candidates(m, b * 32, cand, stride, count);    // GF hittable.h:47, 0.4 % of tests
+    }
+    // tail: up to three groups of 8 slots (the array is padded with zero records to a multiple of 8)
+    if (g.tail_groups) {
+        uint32_t signs = 0;
+#pragma unroll 1
+        for (int part = 0; part < g.tail_groups; ++part, addr += 8u * REC) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const typename N::vec4 s = lds_geom<T>(addr + (uint32_t)k * REC);
+                T h;
+                const T disc = disc_of<T>(s, o, d, a, h);
+                signs = __funnelshift_l(sign_word(disc), signs, 1);
+            }
         }
+        const uint32_t m = (~signs << (32 - 8 * g.tail_groups)) & g.tail_mask;
+        if (m) push_candidates(m, g.blocks * 32, cand, stride, count);
     }
     Hit<T> hit;
     hit.t = N::inf();

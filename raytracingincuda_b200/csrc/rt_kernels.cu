@@ -22,6 +22,9 @@ namespace rt {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TRACE_BLOCK = 256;
+#ifndef RT_TRACE_MIN_BLOCKS
+#define RT_TRACE_MIN_BLOCKS 2
+#endif
 
 template <typename T> struct DevCamera {
     Vec3<T> center, pixel00, du, dv, disk_u, disk_v;
@@ -225,17 +228,14 @@ __device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(TRACE_BLOCK) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
+__global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
     const SceneView<T> sc = view_of<T>(smem, A.scene);
     unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
-    ScanGeom geo;
-    geo.addr = smem_u32(smem);
-    geo.blocks = (A.scene.n + 31) / 32;
-    geo.tail_mask = tail_mask_of(A.scene.n);
+    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene.n);
 
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
@@ -382,10 +382,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
     __shared__ __align__(8) uint64_t bar;
     stage_scene(smem, scene.base, scene.bytes, &bar);
     unsigned short *cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
-    ScanGeom geo;
-    geo.addr = smem_u32(smem);
-    geo.blocks = (scene.n + 31) / 32;
-    geo.tail_mask = tail_mask_of(scene.n);
+    const ScanGeom geo = scan_geom(smem_u32(smem), scene.n);
     const long long npix = (long long)width * height;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(k / width), i = (int)(k - (long long)j * width);
@@ -466,9 +463,9 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     using V4 = typename Num<T>::vec4;
     if (!ctx || !slots || n <= 0 || n > 65535) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
-    const size_t n32 = ((size_t)n + 31) & ~(size_t)31;                    // the scan walks blocks of 32 slots
+    const size_t n8 = ((size_t)n + 7) & ~(size_t)7;                       // the scan's tail walks groups of 8 slots
     const size_t type_bytes = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
-    const size_t geom_bytes = n32 * sizeof(V4);
+    const size_t geom_bytes = n8 * sizeof(V4);
     const size_t matl_bytes = (size_t)n * sizeof(V4);
     const size_t total = geom_bytes + matl_bytes + type_bytes;
     std::vector<unsigned char> host(total, 0);
