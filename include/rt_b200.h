@@ -180,6 +180,9 @@ int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, in
  * (GF hittable.h:80-98).  ids: slot index or -1; t: hit distance or +inf.  Host or device. */
 int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t);
 int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t);
+/* Same pass through the chosen acceleration structure (RT_ACCEL_LBVH builds the tree on the device
+ * on first use); the result is identical to the linear scan's. */
+int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t);
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
 

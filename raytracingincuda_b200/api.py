@@ -87,6 +87,7 @@ SYMBOLS = {
     "rt_finalize": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(C.c_float)]),
     "rt_primary_hits": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
+    "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "rt_get_stats": (C.c_int, [_P, _P]),
 }
 
@@ -179,10 +180,14 @@ def ppm_quantise(rgb):
     return out
 
 
-def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=8, threads=8):
+ACCEL_LINEAR, ACCEL_LBVH = 0, 1
+
+
+def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=8, threads=8, accel=ACCEL_LINEAR):
     o = Opts()
     lib().rt_opts_default(C.byref(o))
     o.seed, o.split, o.rank, o.world, o.tile_rows, o.threads = seed, split, rank, world, tile_rows, threads
+    o.accel = accel
     return o
 
 
@@ -268,10 +273,14 @@ class Renderer:
             "rt_finalize")
         return out
 
-    def primary_hits(self, cam):
+    def primary_hits(self, cam, accel=ACCEL_LINEAR):
         double = isinstance(cam, Camera64)
         ids = np.empty((cam.height, cam.width), dtype=np.int32)
         t = np.empty((cam.height, cam.width), dtype=np.float64 if double else np.float32)
+        if accel != ACCEL_LINEAR:
+            _ck(lib().rt_primary_hits_accel(self._ctx, C.byref(cam), accel, ids.ctypes.data, t.ctypes.data),
+                "rt_primary_hits_accel")
+            return ids, t
         fn = lib().rt_primary_hits64 if double else lib().rt_primary_hits
         _ck(fn(self._ctx, C.byref(cam), ids.ctypes.data, t.ctypes.data), "rt_primary_hits")
         return ids, t

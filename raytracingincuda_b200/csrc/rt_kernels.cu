@@ -12,10 +12,13 @@
 //                    routine (parity probe for GF hittable.h:80-98).
 #include "rt_b200.h"
 #include "rt_device.cuh"
+#include "rt_lbvh.cuh"
 
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace rt {
@@ -43,7 +46,8 @@ template <typename T> struct TraceArgs {
     unsigned long long pix_local;      // pixels rendered by this launch
     unsigned long long total_jobs;     // (c_end - c_begin) * pix_local
     typename Num<T>::vec4 *partial;    // [job]
-    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths
+    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests
+    BvhView bvh;                       // RT_ACCEL_LBVH only
 };
 
 // ------------------------------------------------------------------------------------------
@@ -227,15 +231,25 @@ __device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) 
     return (tile * A.world + A.rank) * A.tile_rows + within;
 }
 
-template <typename T>
+template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
-    stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
-    const SceneView<T> sc = view_of<T>(smem, A.scene);
-    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
-    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene.n);
+    SceneView<T> sc;
+    unsigned short *cand = nullptr;
+    ScanGeom geo = scan_geom(0u, 0);
+    if (ACCEL == RT_ACCEL_LINEAR) {
+        // whole scene -> shared memory, one TMA bulk copy per CTA
+        stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
+        sc = view_of<T>(smem, A.scene);
+        cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
+        geo = scan_geom(smem_u32(smem), A.scene.n);
+    } else {
+        // large scenes: geometry through the LBVH in global memory (L1/L2), materials by slot
+        sc = view_of<T>(A.scene.base, A.scene);
+    }
+    unsigned int n_nodes = 0, n_tests = 0;
 
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
@@ -290,7 +304,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         }
 
         // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
-        const Hit<T> hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+        Hit<T> hit;
+        if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(A.bvh, ps.o, ps.d, n_nodes, n_tests);
+        else hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
 
         // ---- shade ----
         if (state == ACTIVE) {
@@ -331,6 +347,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     if (lane == 0) {
         atomicAdd(A.queue + 1, seg);
         atomicAdd(A.queue + 2, pth);
+    }
+    if (ACCEL == RT_ACCEL_LBVH) {
+        unsigned long long nod = n_nodes, tst = n_tests;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            nod += __shfl_xor_sync(FULL, nod, off);
+            tst += __shfl_xor_sync(FULL, tst, off);
+        }
+        if (lane == 0) { atomicAdd(A.queue + 3, nod); atomicAdd(A.queue + 4, tst); }
     }
 }
 
@@ -373,16 +398,22 @@ __global__ void __launch_bounds__(256) finalize_kernel(const typename Num<T>::ve
 }
 
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_constant__ DevCamera<T> cam,
-                                                              const __grid_constant__ SceneBlob scene, int width,
+                                                              const __grid_constant__ SceneBlob scene,
+                                                              const __grid_constant__ BvhView bvh, int width,
                                                               int height, int *__restrict__ ids, T *__restrict__ ts) {
     using N = Num<T>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
-    stage_scene(smem, scene.base, scene.bytes, &bar);
-    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
-    const ScanGeom geo = scan_geom(smem_u32(smem), scene.n);
+    unsigned short *cand = nullptr;
+    ScanGeom geo = scan_geom(0u, 0);
+    if (ACCEL == RT_ACCEL_LINEAR) {
+        stage_scene(smem, scene.base, scene.bytes, &bar);
+        cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
+        geo = scan_geom(smem_u32(smem), scene.n);
+    }
+    unsigned int n_nodes = 0, n_tests = 0;
     const long long npix = (long long)width * height;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(k / width), i = (int)(k - (long long)j * width);
@@ -391,7 +422,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
         d.x = N::sub(N::fma(fj, cam.dv.x, N::fma(fi, cam.du.x, cam.pixel00.x)), cam.center.x);
         d.y = N::sub(N::fma(fj, cam.dv.y, N::fma(fi, cam.du.y, cam.pixel00.y)), cam.center.y);
         d.z = N::sub(N::fma(fj, cam.dv.z, N::fma(fi, cam.du.z, cam.pixel00.z)), cam.center.z);
-        const Hit<T> hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
+        Hit<T> hit;
+        if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(bvh, cam.center, d, n_nodes, n_tests);
+        else hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
         ids[k] = hit.id;
         ts[k] = hit.t;
     }
@@ -419,9 +452,17 @@ struct rt_ctx {
     size_t partial_bytes = 0;
     void *frame = nullptr;              // device frame when the caller's buffer is host memory
     size_t frame_bytes = 0;
-    unsigned long long *queue = nullptr;   // 4 x u64
+    unsigned long long *queue = nullptr;   // 8 x u64: job cursor + work counters
     rt_stats stats{};
+    // LBVH (float scenes; built on the device the first time RT_ACCEL_LBVH is asked for)
+    std::vector<float4> host_geom;
+    bool bvh_ready = false;
+    BvhView bvh{};
+    void *bvh_mem[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // nodes, geom, slot, big_geom, big_slot
+    float bvh_build_ms = 0.f;
 };
+
+constexpr int QUEUE_WORDS = 8;
 
 #define RT_CUDA(call)                                         \
     do {                                                      \
@@ -461,7 +502,7 @@ template <typename T, typename Cam> DevCamera<T> to_dev(const Cam &c) {
 
 template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, int n) {
     using V4 = typename Num<T>::vec4;
-    if (!ctx || !slots || n <= 0 || n > 65535) return RT_EINVAL;
+    if (!ctx || !slots || n <= 0 || n > (1 << 24)) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;                       // the scan's tail walks groups of 8 slots
     const size_t type_bytes = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
@@ -490,19 +531,124 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     ctx->blob.type_off = (uint32_t)(geom_bytes + matl_bytes);
     ctx->blob.n = n;
     ctx->scene_prec = (int)sizeof(T);
+    // a new scene invalidates the LBVH; keep the float geometry for its host-side classification
+    for (void *&m : ctx->bvh_mem) if (m) { cudaFree(m); m = nullptr; }
+    ctx->bvh_ready = false;
+    ctx->bvh = BvhView{};
+    ctx->host_geom.clear();
+    if (sizeof(T) == 4) {
+        ctx->host_geom.resize((size_t)n);
+        for (int i = 0; i < n; ++i)
+            ctx->host_geom[(size_t)i] = make_float4((float)slots[i].cx, (float)slots[i].cy, (float)slots[i].cz, (float)slots[i].r);
+    }
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LBVH build: classification on the host (which spheres are too big for the tree), everything
+// else -- Morton codes, radix sort, hierarchy, refit -- on the device.
+int build_lbvh(rt_ctx *ctx) {
+    if (ctx->bvh_ready) return RT_OK;
+    if (ctx->scene_prec != 4 || ctx->host_geom.empty()) return RT_EPRECISION;
+    const int n = ctx->blob.n;
+    const std::vector<float4> &g = ctx->host_geom;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (const float4 &s : g) {
+        lo[0] = std::min(lo[0], s.x); lo[1] = std::min(lo[1], s.y); lo[2] = std::min(lo[2], s.z);
+        hi[0] = std::max(hi[0], s.x); hi[1] = std::max(hi[1], s.y); hi[2] = std::max(hi[2], s.z);
+    }
+    const float diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) +
+                                 (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    std::vector<int> small_idx, big_idx;
+    for (int i = 0; i < n; ++i) (g[(size_t)i].w > 0.25f * diag ? big_idx : small_idx).push_back(i);
+    if (big_idx.size() > 64) { small_idx.resize((size_t)n); for (int i = 0; i < n; ++i) small_idx[(size_t)i] = i; big_idx.clear(); }
+    const int m = (int)small_idx.size(), nbig = (int)big_idx.size();
+    for (int q = 0; q < 3; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
+    for (int i : small_idx) {
+        const float4 &s = g[(size_t)i];
+        lo[0] = std::min(lo[0], s.x); lo[1] = std::min(lo[1], s.y); lo[2] = std::min(lo[2], s.z);
+        hi[0] = std::max(hi[0], s.x); hi[1] = std::max(hi[1], s.y); hi[2] = std::max(hi[2], s.z);
+    }
+    const float4 *geom_dev = static_cast<const float4 *>(ctx->scene_dev);
+    cudaStream_t st = ctx->stream;
+    RT_CUDA(cudaEventRecord(ctx->ev[3], st));
+
+    // persistent arrays
+    float4 *nodes = nullptr, *geom_sorted = nullptr, *big_geom = nullptr;
+    int *slot_sorted = nullptr, *big_slot = nullptr;
+    if (nbig) {
+        std::vector<float4> bg((size_t)nbig);
+        for (int b = 0; b < nbig; ++b) bg[(size_t)b] = g[(size_t)big_idx[(size_t)b]];
+        RT_CUDA(cudaMalloc(&big_geom, sizeof(float4) * nbig));
+        RT_CUDA(cudaMalloc(&big_slot, sizeof(int) * nbig));
+        RT_CUDA(cudaMemcpyAsync(big_geom, bg.data(), sizeof(float4) * nbig, cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaMemcpyAsync(big_slot, big_idx.data(), sizeof(int) * nbig, cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+    }
+    if (m > 0) {
+        RT_CUDA(cudaMalloc(&geom_sorted, sizeof(float4) * m));
+        RT_CUDA(cudaMalloc(&slot_sorted, sizeof(int) * m));
+        RT_CUDA(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)std::max(1, m - 1)));
+        // temporaries
+        int *small_dev = nullptr, *vals = nullptr, *parent = nullptr, *flags = nullptr;
+        uint32_t *keys = nullptr, *keys_sorted = nullptr;
+        float *box = nullptr, *rad = nullptr;
+        int2 *children = nullptr;
+        void *cub_tmp = nullptr;
+        size_t cub_bytes = 0;
+        const size_t nn = (size_t)2 * m - 1;
+        RT_CUDA(cudaMalloc(&small_dev, sizeof(int) * m));
+        RT_CUDA(cudaMalloc(&vals, sizeof(int) * m));
+        RT_CUDA(cudaMalloc(&keys, sizeof(uint32_t) * m));
+        RT_CUDA(cudaMalloc(&keys_sorted, sizeof(uint32_t) * m));
+        RT_CUDA(cudaMalloc(&box, sizeof(float) * 6 * nn));
+        RT_CUDA(cudaMalloc(&rad, sizeof(float) * nn));
+        RT_CUDA(cudaMalloc(&parent, sizeof(int) * nn));
+        RT_CUDA(cudaMalloc(&flags, sizeof(int) * std::max(1, m - 1)));
+        RT_CUDA(cudaMalloc(&children, sizeof(int2) * std::max(1, m - 1)));
+        RT_CUDA(cudaMemcpyAsync(small_dev, small_idx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st));
+        const int tb = 256, gb = (m + tb - 1) / tb;
+        const float3 lo3 = make_float3(lo[0], lo[1], lo[2]);
+        const float3 inv3 = make_float3(hi[0] > lo[0] ? 1.f / (hi[0] - lo[0]) : 0.f, hi[1] > lo[1] ? 1.f / (hi[1] - lo[1]) : 0.f,
+                                        hi[2] > lo[2] ? 1.f / (hi[2] - lo[2]) : 0.f);
+        bvh_morton_kernel<<<gb, tb, 0, st>>>(geom_dev, small_dev, m, lo3, inv3, keys, vals);
+        RT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, vals, slot_sorted, m, 0, 30, st));
+        RT_CUDA(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+        RT_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, vals, slot_sorted, m, 0, 30, st));
+        bvh_leaves_kernel<<<gb, tb, 0, st>>>(geom_dev, slot_sorted, m, geom_sorted, box, rad);
+        if (m > 1) {
+            RT_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (m - 1), st));
+            bvh_hierarchy_kernel<<<(m - 1 + tb - 1) / tb, tb, 0, st>>>(keys_sorted, m, children, parent);
+            bvh_refit_kernel<<<gb, tb, 0, st>>>(m, children, parent, box, rad, flags, nodes);
+        }
+        RT_CUDA(cudaGetLastError());
+        RT_CUDA(cudaStreamSynchronize(st));
+        for (void *p : {(void *)small_dev, (void *)vals, (void *)keys, (void *)keys_sorted, (void *)box, (void *)rad,
+                        (void *)parent, (void *)flags, (void *)children, cub_tmp})
+            cudaFree(p);
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev[2], st));
+    RT_CUDA(cudaEventSynchronize(ctx->ev[2]));
+    RT_CUDA(cudaEventElapsedTime(&ctx->bvh_build_ms, ctx->ev[3], ctx->ev[2]));
+    ctx->bvh_mem[0] = nodes; ctx->bvh_mem[1] = geom_sorted; ctx->bvh_mem[2] = slot_sorted;
+    ctx->bvh_mem[3] = big_geom; ctx->bvh_mem[4] = big_slot;
+    ctx->bvh.nodes = nodes; ctx->bvh.geom = geom_sorted; ctx->bvh.slot = slot_sorted;
+    ctx->bvh.big_geom = big_geom; ctx->bvh.big_slot = big_slot;
+    ctx->bvh.m = m; ctx->bvh.nbig = nbig;
+    ctx->bvh_ready = true;
     return RT_OK;
 }
 
 size_t trace_smem(const SceneBlob &b) { return (size_t)b.bytes + (size_t)CAND_CAP * TRACE_BLOCK * sizeof(unsigned short); }
 
-template <typename T> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
-    RT_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <typename T, int ACCEL> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
+    RT_CUDA(cudaFuncSetAttribute(trace_kernel<T, ACCEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<T>, TRACE_BLOCK, smem));
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<T, ACCEL>, TRACE_BLOCK, smem));
     if (per_sm < 1) return RT_EINVAL;
     *grid = ctx->sm_count * per_sm;
     cudaFuncAttributes fa;
-    RT_CUDA(cudaFuncGetAttributes(&fa, trace_kernel<T>));
+    RT_CUDA(cudaFuncGetAttributes(&fa, trace_kernel<T, ACCEL>));
     ctx->stats.regs = fa.numRegs;
     ctx->stats.smem_bytes = (int)(smem + fa.sharedSizeBytes);
     ctx->stats.grid = *grid;
@@ -514,12 +660,17 @@ template <typename T> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
 template <typename T, typename Cam>
 int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
           typename Num<T>::vec4 *partial) {
-    const size_t smem = trace_smem(ctx->blob);
-    if (smem > 227 * 1024) return RT_EINVAL;          // scene too large for the shared-memory scan
+    const bool lbvh = (o.accel == RT_ACCEL_LBVH);
+    if (lbvh && sizeof(T) != 4) return RT_EPRECISION;
+    const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
+    if (smem > 227 * 1024 || (!lbvh && ctx->blob.n > 65535)) return RT_EINVAL;   // too large for the shared-memory scan: use RT_ACCEL_LBVH
     int grid = 0;
-    int rc = launch_shape<T>(ctx, smem, &grid);
+    int rc = lbvh ? build_lbvh(ctx) : RT_OK;
+    if (rc) return rc;
+    rc = lbvh ? launch_shape<T, RT_ACCEL_LBVH>(ctx, smem, &grid) : launch_shape<T, RT_ACCEL_LINEAR>(ctx, smem, &grid);
     if (rc) return rc;
     TraceArgs<T> A;
+    A.bvh = ctx->bvh;
     A.cam = to_dev<T>(cam);
     A.scene = ctx->blob;
     A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
@@ -532,12 +683,13 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
     A.partial = partial;
     A.queue = ctx->queue;
-    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
     if (A.total_jobs == 0) return RT_OK;
     const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
     if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
     ctx->stats.grid = grid;
-    trace_kernel<T><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    if (lbvh) trace_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    else trace_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     RT_CUDA(cudaGetLastError());
     ctx->stats.launches += 1;
     return RT_OK;
@@ -558,18 +710,18 @@ int check_opts(const rt_opts &o) {
     if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return RT_EINVAL;
     if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
-    if (o.accel != RT_ACCEL_LINEAR) return RT_EINVAL;
+    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH) return RT_EINVAL;
     return RT_OK;
 }
 
 int read_counters(rt_ctx *ctx, float ms_total, float ms_trace, int chunks) {
-    unsigned long long h[4];
+    unsigned long long h[QUEUE_WORDS];
     RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.segments = h[1];
     ctx->stats.paths = h[2];
-    ctx->stats.sphere_tests = h[1] * (unsigned long long)ctx->blob.n;
-    ctx->stats.node_visits = 0;
+    ctx->stats.sphere_tests = h[3] || h[4] ? h[4] : h[1] * (unsigned long long)ctx->blob.n;
+    ctx->stats.node_visits = h[3];
     ctx->stats.render_ms = ms_total;
     ctx->stats.trace_ms = ms_trace;
     ctx->stats.chunks = chunks;
@@ -608,7 +760,7 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
     if (cam->max_depth <= 0) {
         // GF camera.h:84,127: no bounce budget -> every path is black
         RT_CUDA(cudaMemsetAsync(frame, 0, out_bytes, ctx->stream));
-        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
         RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     } else {
         rc = ensure(&ctx->partial, &ctx->partial_bytes, (size_t)pix * chunks * sizeof(V4) + 16);
@@ -633,8 +785,10 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
 }
 
 template <typename T, typename Cam>
-int primary_impl(rt_ctx *ctx, const Cam *cam, int32_t *ids, T *t) {
+int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (!ctx || !cam || !ids || !t) return RT_EINVAL;
+    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH) return RT_EINVAL;
+    if (accel == RT_ACCEL_LBVH && sizeof(T) != 4) return RT_EPRECISION;
     if (!ctx->scene_dev) return RT_ENOSCENE;
     if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
     RT_CUDA(cudaSetDevice(ctx->device));
@@ -648,13 +802,23 @@ int primary_impl(rt_ctx *ctx, const Cam *cam, int32_t *ids, T *t) {
         if (!t_dev) d_t = static_cast<T *>(tmp);
         if (!ids_dev) d_ids = reinterpret_cast<int32_t *>(static_cast<char *>(tmp) + npix * sizeof(T));
     }
-    const size_t smem = trace_smem(ctx->blob);
+    const bool lbvh = accel == RT_ACCEL_LBVH;
+    const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
     int rc = RT_OK;
-    cudaError_t e = cudaFuncSetAttribute(primary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!lbvh && (smem > 227 * 1024 || ctx->blob.n > 65535)) rc = RT_EINVAL;
+    if (rc == RT_OK && lbvh) rc = build_lbvh(ctx);
+    if (rc != RT_OK) { if (tmp) cudaFree(tmp); return rc; }
+    cudaError_t e = lbvh ? cudaSuccess
+                         : cudaFuncSetAttribute(primary_kernel<T, RT_ACCEL_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        const int grid = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
-        primary_kernel<T><<<grid < ctx->sm_count * 8 ? grid : ctx->sm_count * 8, TRACE_BLOCK, smem, ctx->stream>>>(
-            to_dev<T>(*cam), ctx->blob, cam->width, cam->height, d_ids, d_t);
+        int grid = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        if (lbvh)
+            primary_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width,
+                                                                                    cam->height, d_ids, d_t);
+        else
+            primary_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh,
+                                                                                         cam->width, cam->height, d_ids, d_t);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && !ids_dev)
@@ -687,7 +851,7 @@ int rt_create(int device, rt_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     ctx->own_stream = (e == cudaSuccess);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->queue), 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->queue), QUEUE_WORDS * sizeof(unsigned long long));
     if (e != cudaSuccess) { rt_destroy(ctx); return (int)e; }
     *out = ctx;
     return RT_OK;
@@ -701,6 +865,7 @@ int rt_destroy(rt_ctx *ctx) {
     if (ctx->partial) cudaFree(ctx->partial);
     if (ctx->frame) cudaFree(ctx->frame);
     if (ctx->queue) cudaFree(ctx->queue);
+    for (void *m : ctx->bvh_mem) if (m) cudaFree(m);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -780,8 +945,15 @@ int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, in
     return RT_OK;
 }
 
-int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t) { return primary_impl<float>(ctx, cam, ids, t); }
-int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t) { return primary_impl<double>(ctx, cam, ids, t); }
+int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t) {
+    return primary_impl<float>(ctx, cam, RT_ACCEL_LINEAR, ids, t);
+}
+int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t) {
+    return primary_impl<double>(ctx, cam, RT_ACCEL_LINEAR, ids, t);
+}
+int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t) {
+    return primary_impl<float>(ctx, cam, accel, ids, t);
+}
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats) {
     if (!ctx || !stats) return RT_EINVAL;

@@ -1,0 +1,231 @@
+// rt_lbvh.cuh -- on-GPU LBVH over the small spheres of a large scene (BASELINE config 5, the
+// "optional LBVH built on-GPU for large sphere counts" of the north star) and a traversal whose
+// result is the one the reference's linear hit_world loop (GF hittable.h:80-98) produces.
+//
+// Build (Karras 2012): Morton codes of the sphere centres -> cub radix sort -> one thread per
+// internal node finds its range and split -> bottom-up refit with one atomic flag per node.
+// Spheres that are huge relative to the scene (the ground sphere) are kept out of the tree in a
+// short "big" list that every ray tests directly.
+//
+// Exactness.  The linear scan's answer is order independent: each sphere contributes
+//   v(S) = first of its two roots that is > tmin,   answer = min v(S), ties -> lowest slot
+// (the reference's shrinking-tmax test accepts S iff v(S) < closest).  The traversal evaluates
+// v(S) with the reference's exact arithmetic (disc_of / roots) at the leaves, so it only has to
+// be CONSERVATIVE about which leaves it visits.  In float the reference's discriminant carries an
+// error of up to ~8 ulp of a*|oc|^2, i.e. a sphere behaves as if its radius^2 were
+// r^2 + 16*eps*D^2 for a ray whose origin is D away -- far-away rays see "noisy" hits around small
+// spheres.  Child boxes are therefore inflated per ray by
+//   delta = sqrt(rmin^2 + KEPS*D^2) - rmin + BEPS*D
+// where D bounds the distance from the ray origin to the box and rmin is the smallest radius
+// below the child, and nodes are culled against best_t with a relative slack.
+#pragma once
+#include "rt_device.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace rt {
+
+struct BvhView {
+    const float4 *nodes;      // 4 x float4 per internal node (see node_store)
+    const float4 *geom;       // [m] small spheres in Morton order
+    const int *slot;          // [m] original slot of each sorted sphere
+    const float4 *big_geom;   // [nbig] spheres kept out of the tree
+    const int *big_slot;
+    int m, nbig;
+};
+
+constexpr float BVH_KEPS = 16.0f * 5.9604645e-8f;   // 16 * 2^-24
+constexpr float BVH_BEPS = 8.0f * 5.9604645e-8f;
+constexpr int BVH_STACK = 64;
+
+// ------------------------------------------------------------------------------ build ------
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void bvh_morton_kernel(const float4 *__restrict__ geom, const int *__restrict__ small_idx, int m,
+                                  float3 lo, float3 inv_extent, uint32_t *__restrict__ keys, int *__restrict__ vals) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int s = small_idx[k];
+    const float4 g = geom[s];
+    const float x = fminf(fmaxf((g.x - lo.x) * inv_extent.x * 1024.0f, 0.0f), 1023.0f);
+    const float y = fminf(fmaxf((g.y - lo.y) * inv_extent.y * 1024.0f, 0.0f), 1023.0f);
+    const float z = fminf(fmaxf((g.z - lo.z) * inv_extent.z * 1024.0f, 0.0f), 1023.0f);
+    keys[k] = (expand_bits10((uint32_t)x) << 2) | (expand_bits10((uint32_t)y) << 1) | expand_bits10((uint32_t)z);
+    vals[k] = s;
+}
+
+// boxes/rad are indexed by "node id": internal nodes 0..m-2, leaves m-1..2m-2
+__global__ void bvh_leaves_kernel(const float4 *__restrict__ geom, const int *__restrict__ sorted_slot, int m,
+                                  float4 *__restrict__ geom_sorted, float *__restrict__ box, float *__restrict__ rad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const float4 g = geom[sorted_slot[k]];
+    geom_sorted[k] = g;
+    float *b = box + 6 * (size_t)(m - 1 + k);
+    b[0] = g.x - g.w; b[1] = g.y - g.w; b[2] = g.z - g.w;
+    b[3] = g.x + g.w; b[4] = g.y + g.w; b[5] = g.z + g.w;
+    rad[m - 1 + k] = g.w;
+}
+
+__device__ __forceinline__ int bvh_delta(const uint32_t *__restrict__ keys, int m, int i, int j) {
+    if (j < 0 || j >= m) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    return a == b ? 32 + __clz((uint32_t)i ^ (uint32_t)j) : __clz(a ^ b);
+}
+
+// child encoding: >= 0 internal node, < 0 leaf (~value = sorted index)
+__global__ void bvh_hierarchy_kernel(const uint32_t *__restrict__ keys, int m, int2 *__restrict__ children,
+                                     int *__restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m - 1) return;
+    const int d = bvh_delta(keys, m, i, i + 1) - bvh_delta(keys, m, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = bvh_delta(keys, m, i, i - d);
+    int lmax = 2;
+    while (bvh_delta(keys, m, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (bvh_delta(keys, m, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = bvh_delta(keys, m, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (bvh_delta(keys, m, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = (lo == gamma) ? ~gamma : gamma;
+    const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    parent[left < 0 ? (m - 1 + ~left) : left] = i;
+    parent[right < 0 ? (m - 1 + ~right) : right] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__global__ void bvh_refit_kernel(int m, const int2 *__restrict__ children, const int *__restrict__ parent,
+                                 float *box, float *rad, int *flags, float4 *__restrict__ nodes) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    int node = parent[m - 1 + k];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1) == 0) return;          // the sibling subtree is not done yet
+        const int2 ch = children[node];
+        const int li = ch.x < 0 ? (m - 1 + ~ch.x) : ch.x, ri = ch.y < 0 ? (m - 1 + ~ch.y) : ch.y;
+        const volatile float *bl = box + 6 * (size_t)li, *br = box + 6 * (size_t)ri;
+        float l[6], r[6];
+        for (int q = 0; q < 6; ++q) { l[q] = bl[q]; r[q] = br[q]; }
+        const float rl = ((volatile float *)rad)[li], rr = ((volatile float *)rad)[ri];
+        float *bn = box + 6 * (size_t)node;
+        for (int q = 0; q < 3; ++q) { bn[q] = fminf(l[q], r[q]); bn[q + 3] = fmaxf(l[q + 3], r[q + 3]); }
+        rad[node] = fminf(rl, rr);
+        // node record: lmin.xyz lmax.x | lmax.yz rmin.xy | rmin.z rmax.xyz | left right lrad rrad
+        nodes[4 * (size_t)node + 0] = make_float4(l[0], l[1], l[2], l[3]);
+        nodes[4 * (size_t)node + 1] = make_float4(l[4], l[5], r[0], r[1]);
+        nodes[4 * (size_t)node + 2] = make_float4(r[2], r[3], r[4], r[5]);
+        nodes[4 * (size_t)node + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), rl, rr);
+        node = parent[node];
+    }
+}
+
+// ------------------------------------------------------------------------------ traversal ---
+// exact sphere test with the order-independent acceptance rule (see the header comment)
+__device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const Vec3<float> &o, const Vec3<float> &d,
+                                                float a, Hit<float> &hit) {
+    using N = Num<float>;
+    float h;
+    const float disc = disc_of<float>(s, o, d, a, h);
+    if (disc < 0.0f) return;
+    const float sq = N::sqrt(disc);
+    float v = N::div(N::sub(h, sq), a);
+    if (!(N::tmin() < v)) {
+        v = N::div(N::add(h, sq), a);
+        if (!(N::tmin() < v)) return;
+    }
+    if (v < hit.t || (v == hit.t && slot < hit.id)) { hit.t = v; hit.id = slot; }
+}
+
+// entry parameter of the inflated box, or +inf when the ray cannot touch it before `limit`
+__device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, float hx, float hy, float hz, float rmin,
+                                               const Vec3<float> &o, const Vec3<float> &inv, float limit) {
+    const float fx = fmaxf(fabsf(lx - o.x), fabsf(hx - o.x));
+    const float fy = fmaxf(fabsf(ly - o.y), fabsf(hy - o.y));
+    const float fz = fmaxf(fabsf(lz - o.z), fabsf(hz - o.z));
+    const float D2 = fx * fx + fy * fy + fz * fz;
+    const float delta = (sqrtf(rmin * rmin + BVH_KEPS * D2) - rmin) * 1.001f + BVH_BEPS * sqrtf(D2);
+    const float t0x = (lx - delta - o.x) * inv.x, t1x = (hx + delta - o.x) * inv.x;
+    const float t0y = (ly - delta - o.y) * inv.y, t1y = (hy + delta - o.y) * inv.y;
+    const float t0z = (lz - delta - o.z) * inv.z, t1z = (hz + delta - o.z) * inv.z;
+    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    const bool ok = tn <= tf * 1.00001f + 1e-30f && tf >= 0.0f && tn <= limit;
+    return ok ? tn : __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ Hit<float> bvh_closest_hit(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d,
+                                                      unsigned &n_nodes, unsigned &n_tests) {
+    using N = Num<float>;
+    const float a = dot3(d, d);
+    Hit<float> hit;
+    hit.t = N::inf();
+    hit.id = -1;
+    for (int b = 0; b < bv.nbig; ++b) bvh_test_sphere(__ldg(bv.big_geom + b), __ldg(bv.big_slot + b), o, d, a, hit);
+    n_tests += bv.nbig;
+    if (bv.m == 0) return hit;
+    if (bv.m == 1) {
+        bvh_test_sphere(__ldg(bv.geom), __ldg(bv.slot), o, d, a, hit);
+        ++n_tests;
+        return hit;
+    }
+    Vec3<float> inv;
+    inv.x = 1.0f / d.x; inv.y = 1.0f / d.y; inv.z = 1.0f / d.z;
+    int stack[BVH_STACK];
+    float tstack[BVH_STACK];
+    int sp = 0, node = 0;
+    const float inf = N::inf();
+    for (;;) {
+        ++n_nodes;
+        const float4 q0 = __ldg(bv.nodes + 4 * (size_t)node), q1 = __ldg(bv.nodes + 4 * (size_t)node + 1);
+        const float4 q2 = __ldg(bv.nodes + 4 * (size_t)node + 2), q3 = __ldg(bv.nodes + 4 * (size_t)node + 3);
+        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+        const float limit = hit.t * 1.0001f + 1e-6f;
+        float tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, inv, limit);
+        float tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, inv, limit);
+        if (tl < inf && left < 0) {
+            bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, a, hit);
+            ++n_tests;
+            tl = inf;
+        }
+        if (tr < inf && right < 0) {
+            bvh_test_sphere(__ldg(bv.geom + ~right), __ldg(bv.slot + ~right), o, d, a, hit);
+            ++n_tests;
+            tr = inf;
+        }
+        if (tl < inf && tr < inf) {
+            const bool left_first = tl <= tr;
+            stack[sp] = left_first ? right : left;
+            tstack[sp] = left_first ? tr : tl;
+            ++sp;
+            node = left_first ? left : right;
+            continue;
+        }
+        if (tl < inf) { node = left; continue; }
+        if (tr < inf) { node = right; continue; }
+        // pop, skipping subtrees the current best hit already rules out
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (tstack[sp] <= hit.t * 1.0001f + 1e-6f) { node = stack[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    return hit;
+}
+
+}  // namespace rt

@@ -231,3 +231,72 @@ def test_slot_counts_around_block_boundaries(renderer, n):
     img = renderer.render(cam)
     ref, _ = O.render(slots, O.camera(64, 40, 4, 8))
     assert np.array_equal(bits(img), bits(ref))
+
+
+# ------------------------------------------------------------------ LBVH (RT_ACCEL_LBVH) ------
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+def test_lbvh_primary_equals_linear_scan(renderer, scene_id):
+    renderer.upload_scene(rt.scene(scene_id))
+    cam = rt.camera(320, 192)
+    ids, t = renderer.primary_hits(cam)
+    bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
+    assert np.array_equal(ids, bids)
+    assert np.array_equal(bits(t), bits(bt))
+
+
+@pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 96, 64, 8, 25), (3, 64, 40, 16, 50)])
+def test_lbvh_render_equals_linear_scan(renderer, scene_id, w, h, spp, depth):
+    """Same hits => same paths => the same image, bit for bit."""
+    renderer.upload_scene(rt.scene(scene_id))
+    cam = rt.camera(w, h, spp, depth)
+    a = renderer.render(cam)
+    seg = renderer.stats().segments
+    b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
+    st = renderer.stats()
+    assert st.segments == seg and st.node_visits > 0 and 0 < st.sphere_tests < seg * 488
+    assert np.array_equal(bits(a), bits(b))
+
+
+def test_lbvh_mid_size_scene_equals_linear_scan(renderer):
+    """3 604 slots still fit the shared-memory scan: LBVH and linear scan must agree exactly."""
+    slots = rt.scene_scaled(30)
+    assert len(slots) == 3604
+    renderer.upload_scene(slots)
+    cam = rt.camera(160, 96, 4, 10)
+    ids, t = renderer.primary_hits(cam)
+    bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
+    assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
+    a = renderer.render(cam)
+    b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
+    assert np.array_equal(bits(a), bits(b))
+
+
+def test_lbvh_100k_scene_primary_vs_oracle(renderer):
+    """BASELINE config 5 scene (99 860 slots): LBVH primary (slot id, t) against the oracle's
+    linear hit_world, bit for bit."""
+    slots = rt.scene_scaled(158)
+    assert len(slots) == 99860
+    assert slots.tobytes() == O.scene_scaled(158).tobytes()
+    renderer.upload_scene(slots)
+    cam = rt.camera(128, 72)
+    ids, t = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
+    oids, ot = O.primary(slots, O.camera(128, 72))
+    assert np.array_equal(ids, oids)
+    assert np.array_equal(bits(t), bits(ot))
+    with pytest.raises(rt.RtError):
+        renderer.primary_hits(cam)                    # too large for the shared-memory scan
+    img = renderer.render(rt.camera(128, 72, 2, 8), api.make_opts(accel=api.ACCEL_LBVH))
+    ref, seg = O.render(slots, O.camera(128, 72, 2, 8))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(img), bits(ref))
+
+
+def test_lbvh_degenerate_scenes(renderer):
+    """1 and 2 slots, duplicates (equal Morton codes), and the concentric shells."""
+    base = rt.scene(1)
+    for slots in (base[:1].copy(), base[:2].copy(), np.concatenate([base[5:6]] * 7 + [base[:1]]), concentric_scene(40)):
+        renderer.upload_scene(slots)
+        cam = rt.camera(64, 40)
+        ids, t = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
+        oids, ot = O.primary(slots, O.camera(64, 40))
+        assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
