@@ -4,7 +4,7 @@
 // Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
 // setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
 // (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
-// (--seed, --precision, --gpus, --split, --prefix, --no-ppm, --stats) defaults to the reference's
+// (--seed, --precision, --gpus, --accel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
 // behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
 // (global_float_benchmark.sh:53-74) stays valid.
 #include "rt_b200.h"
@@ -50,8 +50,8 @@ struct Args {
     int scene_id = 0, width = 320, height = 192, samples = 10, bounces = 25, threads = 8;
     // extensions
     unsigned long long seed = 1227;
-    bool use_double = false, no_ppm = false, stats = false;
-    int gpus = 1;
+    bool use_double = false, no_ppm = false, stats = false, lbvh = false;
+    int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix;
 };
 
@@ -79,7 +79,7 @@ Args parse(int argc, char **argv) {
         if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
         const bool flag_only = (name == "no-ppm" || name == "stats");
         static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
-                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats"};
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half"};
         bool ok = false;
         for (const char *n : known) ok = ok || name == n;
         if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
@@ -98,6 +98,8 @@ Args parse(int argc, char **argv) {
         else if (name == "gpus") a.gpus = to_int(name, value);
         else if (name == "split") a.split = value;
         else if (name == "prefix") a.prefix = value;
+        else if (name == "accel") a.lbvh = (value == "lbvh");
+        else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; }
         else if (name == "no-ppm") a.no_ppm = true;
         else if (name == "stats") a.stats = true;
     }
@@ -158,9 +160,12 @@ int main(int argc, char **argv) {
         for (auto &d : dev) CHECK(rt_upload_scene64(d.ctx, slots64.data(), n));
         frame64.resize(npix * 3);
     } else {
-        n = rt_scene_generate(a.scene_id, nullptr, 0);
+        // --scaled_half H: the scaled scene of BASELINE config 5 (grid [-H,H)^2) instead of scene_id
+        n = a.scaled_half > 0 ? rt_scene_generate_scaled(a.scaled_half, nullptr, 0) : rt_scene_generate(a.scene_id, nullptr, 0);
+        if (n <= 0) { std::cerr << "Error: bad --scaled_half" << "\n"; return 1; }
         slots.resize(static_cast<size_t>(n));
-        rt_scene_generate(a.scene_id, slots.data(), n);
+        if (a.scaled_half > 0) rt_scene_generate_scaled(a.scaled_half, slots.data(), n);
+        else rt_scene_generate(a.scene_id, slots.data(), n);
         for (auto &d : dev) CHECK(rt_upload_scene(d.ctx, slots.data(), n));
         frame.resize(npix * 3);
     }
@@ -180,6 +185,7 @@ int main(int argc, char **argv) {
             rt_opts_default(&o);
             o.seed = a.seed;
             o.threads = a.threads;
+            o.accel = a.lbvh ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
             if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
             d.rows.resize(static_cast<size_t>(nrows));
@@ -235,8 +241,10 @@ int main(int argc, char **argv) {
         const double mps = static_cast<double>(npix) * a.samples / (render_ms * 1e-3) / 1e6;
         std::fprintf(stderr,
                      "{\"mpath_samples_per_s\": %.3f, \"paths\": %llu, \"segments\": %llu, \"slots\": %d, "
-                     "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d}\n",
-                     mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks);
+                     "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d, "
+                     "\"accel\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu}\n",
+                     mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks,
+                     a.lbvh ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests);
     }
     return 0;
 }
