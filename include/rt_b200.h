@@ -86,7 +86,7 @@ typedef struct rt_opts {
     uint64_t seed;        /* Philox key; default 1227 (the reference's curand seed, GF rtweekend.h:49) */
     int32_t split;        /* RT_SPLIT_*: which part of the frame this context renders */
     int32_t rank, world;  /* this context's index / number of partitions (1 = whole frame) */
-    int32_t tile_rows;    /* RT_SPLIT_ROWS: rows per interleaved tile (default 8) */
+    int32_t tile_rows;    /* RT_SPLIT_ROWS: rows per interleaved tile (default 1: row j -> rank j mod world) */
     int32_t accel;        /* RT_ACCEL_* */
     int32_t threads;      /* the reference's --threads; accepted and ignored by the persistent kernel */
     int32_t reserved[8];

@@ -183,7 +183,7 @@ def ppm_quantise(rgb):
 ACCEL_LINEAR, ACCEL_LBVH = 0, 1
 
 
-def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=8, threads=8, accel=ACCEL_LINEAR):
+def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_LINEAR):
     o = Opts()
     lib().rt_opts_default(C.byref(o))
     o.seed, o.split, o.rank, o.world, o.tile_rows, o.threads = seed, split, rank, world, tile_rows, threads

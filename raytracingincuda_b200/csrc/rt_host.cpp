@@ -274,7 +274,7 @@ void rt_opts_default(rt_opts *opts) {
     opts->split = RT_SPLIT_NONE;
     opts->rank = 0;
     opts->world = 1;
-    opts->tile_rows = 8;
+    opts->tile_rows = 1;
     opts->accel = RT_ACCEL_LINEAR;
     opts->threads = 8;
 }

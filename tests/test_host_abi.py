@@ -147,3 +147,27 @@ def test_cli_matches_reference_binary_text(tmp_path):
         assert (mine.returncode, mine.stdout, mine.stderr) == (ref.returncode, ref.stdout, ref.stderr)
     mine, ref = run([CLI, "--nope", "1"], tmp_path), run([REF_CLI, "--nope", "1"], tmp_path)
     assert mine.returncode == ref.returncode and mine.stderr == ref.stderr
+
+
+def test_ppm_compare_tool(tmp_path):
+    """The scalar comparator of the parity gate: MAE / PSNR / max-abs over code values, diff image."""
+    exe = os.path.join(ROOT, "raytracingincuda_b200", "bin", "ppm-compare")
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, (9, 11, 3)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.003, a.shape), 0, 1).astype(np.float32)
+    c = np.clip(a + 0.2, 0, 1).astype(np.float32)
+    for name, img in (("a", a), ("b", b), ("c", c)):
+        rt.ppm_write(str(tmp_path / f"{name}.ppm"), img)
+    r = run([exe, "a.ppm", "b.ppm", "d.ppm"], tmp_path)
+    out = json.loads(r.stdout)
+    qa, qb = rt.ppm_quantise(a).astype(int), rt.ppm_quantise(b).astype(int)
+    assert r.returncode == 0 and out["within_tolerance"]
+    assert np.allclose(out["mae"], np.abs(qa - qb).mean(axis=(0, 1)), atol=1e-5)
+    assert out["max_abs"] == np.abs(qa - qb).max()
+    mse = ((qa - qb) ** 2).mean()
+    assert abs(out["psnr_db"] - 10 * np.log10(255 ** 2 / mse)) < 1e-3
+    diff = np.array((tmp_path / "d.ppm").read_text().split()[4:], dtype=int).reshape(9, 11, 3)
+    assert np.array_equal(diff, np.abs(qa - qb))
+    r = run([exe, "a.ppm", "c.ppm"], tmp_path)
+    assert r.returncode == 3 and not json.loads(r.stdout)["within_tolerance"]
+    assert run([exe, "a.ppm", "missing.ppm"], tmp_path).returncode == 1
