@@ -98,18 +98,20 @@ struct Philox {
 //                        (the only array the scan reads)
 //   [vec4 matl[n]]       albedo.xyz, param (fuzz for metal, refraction index for dielectric)
 //   [int  type[n4]]
+//   [T    rinv[n]]       1/radius (host IEEE division, the value rcp.rn gives on the device)
 // staged into shared memory by one thread with cp.async.bulk + an mbarrier (TMA bulk copy).
 template <typename T> struct SceneView {
     const typename Num<T>::vec4 *geom;
     const typename Num<T>::vec4 *matl;
     const int *type;
+    const T *rinv;
     int n;
 };
 
 struct SceneBlob {
     const void *base;       // device pointer
     uint32_t bytes;         // multiple of 16
-    uint32_t matl_off, type_off;
+    uint32_t matl_off, type_off, rinv_off;
     int n;
 };
 
@@ -120,6 +122,7 @@ __device__ __forceinline__ SceneView<T> view_of(const void *base, const SceneBlo
     v.geom = reinterpret_cast<const typename Num<T>::vec4 *>(p);
     v.matl = reinterpret_cast<const typename Num<T>::vec4 *>(p + b.matl_off);
     v.type = reinterpret_cast<const int *>(p + b.type_off);
+    v.rinv = reinterpret_cast<const T *>(p + b.rinv_off);
     v.n = b.n;
     return v;
 }

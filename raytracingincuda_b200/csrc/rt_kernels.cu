@@ -56,14 +56,11 @@ template <typename T> struct PathState {
     T puy;                // y of the normalised PRIMARY direction (sky term, GF camera.h:121)
 };
 
-// get_ray (GF camera.h:145-155) with Philox dimension 0 of (pixel, sample)
+// get_ray (GF camera.h:145-155) with Philox dimension 0 of (pixel, sample).
+// `ph` is opened on (pixel, sample, 0) and already holds block 0.
 template <typename T>
-__device__ __forceinline__ void camera_ray(const TraceArgs<T> &A, int i, int j, uint32_t pixel, uint32_t sample,
-                                           PathState<T> &ps) {
+__device__ __forceinline__ void camera_ray(const TraceArgs<T> &A, int i, int j, Philox &ph, PathState<T> &ps) {
     using N = Num<T>;
-    Philox ph;
-    ph.open(A.seed_lo, A.seed_hi, pixel, sample, 0u);
-    ph.block(0);
     T ux, uy;
     if (N::words_per_uniform == 1) { ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); }
     else { ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]); }
@@ -122,7 +119,7 @@ template <> __device__ __forceinline__ void sky<double>(double puy, double &r, d
 }
 
 // random_unit_vector (GF vec3.h:117-127), Philox dimension depth+1, one candidate per block
-// (float) or per two blocks (double)
+// (float) or per two blocks (double).  `ph` already holds block 0.
 template <typename T>
 __device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
     using N = Num<T>;
@@ -130,10 +127,10 @@ __device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
     for (uint32_t k = 0;; ++k) {
         T ux, uy, uz;
         if (N::words_per_uniform == 1) {
-            ph.block(k);
+            if (k > 0) ph.block(k);
             ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
         } else {
-            ph.block(2u * k);
+            if (k > 0) ph.block(2u * k);
             ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
             ph.block(2u * k + 1u);
             uz = N::uniform(ph.w[0], ph.w[1]);
@@ -149,10 +146,10 @@ __device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
 }
 
 // One bounce: hit record (GF hittable.h:58-63) + the material switch of GF camera.h:92-108.
+// `ph` is opened on (pixel, sample, depth+1) and already holds block 0.
 // Returns false when the path is absorbed (metal scattered below the surface, GF material.h:58).
 template <typename T>
-__device__ __forceinline__ bool scatter(const TraceArgs<T> &A, const SceneView<T> &sc, const Hit<T> &hit,
-                                        uint32_t pixel, uint32_t sample, int depth, PathState<T> &ps) {
+__device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hit, Philox &ph, PathState<T> &ps) {
     using N = Num<T>;
     const typename N::vec4 s = sc.geom[hit.id];
     const typename N::vec4 m = sc.matl[hit.id];
@@ -160,14 +157,12 @@ __device__ __forceinline__ bool scatter(const TraceArgs<T> &A, const SceneView<T
     const Vec3<T> o = ps.o, d = ps.d;
     Vec3<T> p;
     p.x = N::fma(hit.t, d.x, o.x); p.y = N::fma(hit.t, d.y, o.y); p.z = N::fma(hit.t, d.z, o.z);
-    const T inv_r = N::rcp(s.w);
+    const T inv_r = sc.rinv[hit.id];                            // 1/radius, rounded once on the host (== rcp.rn)
     Vec3<T> n;
     n.x = N::mul(N::sub(p.x, s.x), inv_r); n.y = N::mul(N::sub(p.y, s.y), inv_r); n.z = N::mul(N::sub(p.z, s.z), inv_r);
     const bool front = dot3(d, n) < T(0);
     if (!front) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
 
-    Philox ph;
-    ph.open(A.seed_lo, A.seed_hi, pixel, sample, static_cast<uint32_t>(depth + 1));
     Vec3<T> nd;
     if (type == RT_DIELECTRIC) {
         // dieletric_scatter (GF material.h:68-89), reflect/refract (GF vec3.h:129-138)
@@ -186,7 +181,6 @@ __device__ __forceinline__ bool scatter(const TraceArgs<T> &A, const SceneView<T
             r0 = N::mul(r0, r0);
             const T x1 = N::sub(T(1), cos_t), x2 = N::mul(x1, x1), x4 = N::mul(x2, x2), x5 = N::mul(x4, x1);
             const T refl = N::fma(N::sub(T(1), r0), x5, r0);
-            ph.block(0);
             reflect = refl > N::uniform(ph.w[0], ph.w[1]);
         }
         if (reflect) {
@@ -254,17 +248,35 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
     int state = NEED_JOB;
-    bool fresh = false;                 // next loop turn starts a new sample
+    bool fresh = false;                 // this lane starts a new sample at the top of the next turn
     PathState<T> ps;
     ps.o = A.cam.center;
     ps.d.x = T(0); ps.d.y = T(1); ps.d.z = T(0);
     ps.att.x = ps.att.y = ps.att.z = T(1);
     ps.puy = T(0);
+    Hit<T> hit;                         // pending hit of the previous turn's scan
+    hit.t = N::inf();
+    hit.id = -1;
     T acc_r = T(0), acc_g = T(0), acc_b = T(0);
     int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
     uint32_t pixel = 0;
     unsigned long long job = 0;
     unsigned int n_seg = 0, n_path = 0;
+
+    // a path ended with radiance (cr,cg,cb): accumulate (GF camera.h:160), move to the next sample
+    // of the job or hand the job's sum back
+    auto end_path = [&](T cr, T cg, T cb) {
+        acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);
+        ++n_path;
+        if (++sample == sample_end) {
+            typename N::vec4 v;
+            v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
+            A.partial[job] = v;
+            state = NEED_JOB;
+        } else {
+            fresh = true;
+        }
+    };
 
     for (;;) {
         // ---- job fetch: one atomic per warp for all lanes that ran out of work ----
@@ -296,43 +308,40 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         }
         if (__all_sync(FULL, state == DEAD)) break;
 
+        // ---- one Philox block per lane and turn, shared by the two consumers: dimension 0 feeds
+        //      the camera ray of a fresh sample, dimension depth+1 the scatter of the pending hit ----
+        Philox ph;
+        ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, fresh ? 0u : (uint32_t)(depth + 1));
+        ph.block(0);
+        if (state == ACTIVE && !fresh) {
+            // shade the hit found by the previous turn's scan
+            const bool alive = scatter(sc, hit, ph, ps);
+            if (!alive || ++depth >= A.max_depth) {                       // GF camera.h:117 / :84,127 -> black
+                end_path(T(0), T(0), T(0));
+                if (state == ACTIVE) {                                    // rare: regenerate right away
+                    ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, 0u);
+                    ph.block(0);
+                }
+            }
+        }
         // ---- path regeneration: a finished lane starts its next sample in place ----
         if (state == ACTIVE && fresh) {
-            camera_ray(A, pi, pj, pixel, (uint32_t)sample, ps);
+            camera_ray(A, pi, pj, ph, ps);
             depth = 0;
             fresh = false;
         }
 
         // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
-        Hit<T> hit;
         if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(A.bvh, ps.o, ps.d, n_nodes, n_tests);
         else hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
 
-        // ---- shade ----
+        // ---- misses end the path here (no random numbers needed); hits are shaded next turn ----
         if (state == ACTIVE) {
             ++n_seg;
-            bool done;
-            T cr = T(0), cg = T(0), cb = T(0);
             if (hit.id < 0) {
                 T sr, sg, sb;
                 sky<T>(ps.puy, sr, sg, sb);
-                cr = N::mul(ps.att.x, sr); cg = N::mul(ps.att.y, sg); cb = N::mul(ps.att.z, sb);
-                done = true;
-            } else {
-                done = !scatter(A, sc, hit, pixel, (uint32_t)sample, depth, ps);
-                if (!done && ++depth >= A.max_depth) done = true;       // GF camera.h:84,127
-            }
-            if (done) {
-                acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);   // GF camera.h:160
-                ++n_path;
-                if (++sample == sample_end) {
-                    typename N::vec4 v;
-                    v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
-                    A.partial[job] = v;
-                    state = NEED_JOB;
-                } else {
-                    fresh = true;
-                }
+                end_path(N::mul(ps.att.x, sr), N::mul(ps.att.y, sg), N::mul(ps.att.z, sb));
             }
         }
     }
@@ -508,11 +517,13 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     const size_t type_bytes = ((size_t)n * sizeof(int) + 15) & ~(size_t)15;
     const size_t geom_bytes = n8 * sizeof(V4);
     const size_t matl_bytes = (size_t)n * sizeof(V4);
-    const size_t total = geom_bytes + matl_bytes + type_bytes;
+    const size_t rinv_bytes = ((size_t)n * sizeof(T) + 15) & ~(size_t)15;
+    const size_t total = geom_bytes + matl_bytes + type_bytes + rinv_bytes;
     std::vector<unsigned char> host(total, 0);
     V4 *geom = reinterpret_cast<V4 *>(host.data());
     V4 *matl = reinterpret_cast<V4 *>(host.data() + geom_bytes);
     int *type = reinterpret_cast<int *>(host.data() + geom_bytes + matl_bytes);
+    T *rinv = reinterpret_cast<T *>(host.data() + geom_bytes + matl_bytes + type_bytes);
     for (int i = 0; i < n; ++i) {
         const Slot &s = slots[i];
         if (s.type < 0 || s.type > 2) return RT_EINVAL;
@@ -520,6 +531,7 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
         matl[i].x = s.albedo[0]; matl[i].y = s.albedo[1]; matl[i].z = s.albedo[2];
         matl[i].w = s.type == RT_METAL ? s.fuzz : (s.type == RT_DIELECTRIC ? s.ri : T(0));
         type[i] = s.type;
+        rinv[i] = T(1) / static_cast<T>(s.r);                    // IEEE division == the device's rcp.rn
     }
     if (ctx->scene_dev) { RT_CUDA(cudaFree(ctx->scene_dev)); ctx->scene_dev = nullptr; }
     RT_CUDA(cudaMalloc(&ctx->scene_dev, total));
@@ -529,6 +541,7 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     ctx->blob.bytes = (uint32_t)total;
     ctx->blob.matl_off = (uint32_t)geom_bytes;
     ctx->blob.type_off = (uint32_t)(geom_bytes + matl_bytes);
+    ctx->blob.rinv_off = (uint32_t)(geom_bytes + matl_bytes + type_bytes);
     ctx->blob.n = n;
     ctx->scene_prec = (int)sizeof(T);
     // a new scene invalidates the LBVH; keep the float geometry for its host-side classification
