@@ -376,6 +376,18 @@ def main():
                          "fp32_instr_frac": round(achieved / peak * 24 / 18, 4),
                          "kernel_ms": round(step_trace_ms, 3), "traffic": None},
         }
+        # DRAM bytes per trace_kernel launch from the committed ncu pass over this same command
+        # (profiles/r01_bench_kernel_traffic.json); None for workloads that were not captured
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_bench_kernel_traffic.json")) as f:
+                cap = json.load(f).get(args.workload, {})
+            k = next(v for name, v in cap.items() if "trace_kernel" in name)
+            if world == 1 and not lbvh:
+                line["roofline"]["traffic"] = int(k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"])
+                line["roofline"]["traffic_note"] = ("ncu dram__bytes_read+write per launch; algorithmic HBM bytes are the "
+                                                    f"{chunks}x{W}x{H}x16 B partial planes written once = {chunks * W * H * 16} B")
+        except Exception:
+            pass
         st = r.stats()
         line["kernel"] = {"grid": st.grid, "block": st.block, "regs": st.regs, "smem_bytes": st.smem_bytes,
                           "segments_per_path": round(segments / paths, 4)}
