@@ -35,6 +35,15 @@ WORKLOADS = {
     "cfg5": (-158, 3840, 2160, 256, 50),
 }
 METRIC = "Mpath-samples/s"
+SLOTS = {1: 488, 2: 40, 3: 125}
+
+
+def workload_name(name):
+    """The same string in both arms' `config.workload`."""
+    scene, W, H, spp, depth = WORKLOADS[name]
+    what = (f"scaled random-spheres scene, grid [-{-scene},{-scene})^2 ({1 + 4 * scene * scene + 3} slots)" if scene < 0
+            else f"scene {scene} final random spheres ({SLOTS[scene]} slots)")
+    return f"{what}, {W}x{H}, {spp} spp, {depth} bounces"
 FLOP_PER_TEST = 18          # SURVEY.md section 8d: 3 FADD + 3 FMUL + 6 FFMA per sphere test
 SM_COUNT, FP32_LANES = 148, 128
 
@@ -177,7 +186,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": METRIC, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"scene {scene}, {W}x{H}, {spp} spp, {depth} bounces (BASELINE configs[3])",
+        "config": {"workload": workload_name(args.workload), "implementation": "serial CPU src/InOneWeekend (double)",
                    "sample": sample},
         "cpu_baseline": {"value": round(val, 4), "unit": METRIC, "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": round(val, 4), "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -332,8 +341,6 @@ def main():
         value = paths / (ms_per_step * 1e-3) / 1e6
         e2e_value = paths / (e2e_ms / args.steps * 1e-3) / 1e6
         n_slots = len(slots)
-        scene_name = (f"scaled random-spheres scene, grid [-{-scene_id},{-scene_id})^2" if scene_id < 0
-                      else f"scene {scene_id} (final random spheres)")
         clk = clocks.summary()
         # linear scan: segments x slots tests; LBVH: the leaf/big tests the traversal actually made
         flop = sphere_tests * FLOP_PER_TEST                             # whole job, one step
@@ -357,8 +364,9 @@ def main():
             "metric": METRIC, "value": round(value, 3), "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{scene_name} ({n_slots} slots), {W}x{H}, {spp} spp, "
-                                   f"{depth} bounces, float, {'on-GPU LBVH' if lbvh else 'linear scan'}", "l2": "inputs regenerate per step; "
+            "config": {"workload": workload_name(args.workload),
+                       "implementation": f"float, {'on-GPU LBVH' if lbvh else 'linear scan in shared memory'}",
+                       "l2": "inputs regenerate per step; "
                                    f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": args.split if world > 1 else "none",
                        "chunks": chunks, "seed": 1227},
             "render_ms": round(ms_per_step, 3),
