@@ -80,6 +80,7 @@ typedef struct rt_camera64 {
 
 enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
 enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1 };
+enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 
 /* Per-call options.  Zero-initialise, then set what you need (rt_opts_default does that). */
 typedef struct rt_opts {
@@ -89,7 +90,9 @@ typedef struct rt_opts {
     int32_t tile_rows;    /* RT_SPLIT_ROWS: rows per interleaved tile (default 1: row j -> rank j mod world) */
     int32_t accel;        /* RT_ACCEL_* */
     int32_t threads;      /* the reference's --threads; accepted and ignored by the persistent kernel */
-    int32_t reserved[8];
+    int32_t kernel;       /* RT_KERNEL_*: persistent megakernel (default) or the material-sorted wavefront
+                           * variant (float, linear scan); both produce the same image bit for bit */
+    int32_t reserved[7];
 } rt_opts;
 
 typedef struct rt_stats {

@@ -48,8 +48,8 @@ class Camera64(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("split", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("tile_rows", C.c_int32), ("accel", C.c_int32), ("threads", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("tile_rows", C.c_int32), ("accel", C.c_int32), ("threads", C.c_int32), ("kernel", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
 
 
 class Stats(C.Structure):
@@ -181,13 +181,15 @@ def ppm_quantise(rgb):
 
 
 ACCEL_LINEAR, ACCEL_LBVH = 0, 1
+KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
 
 
-def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_LINEAR):
+def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_LINEAR,
+              kernel=KERNEL_MEGA):
     o = Opts()
     lib().rt_opts_default(C.byref(o))
     o.seed, o.split, o.rank, o.world, o.tile_rows, o.threads = seed, split, rank, world, tile_rows, threads
-    o.accel = accel
+    o.accel, o.kernel = accel, kernel
     return o
 
 

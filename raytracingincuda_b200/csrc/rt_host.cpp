@@ -277,6 +277,7 @@ void rt_opts_default(rt_opts *opts) {
     opts->tile_rows = 1;
     opts->accel = RT_ACCEL_LINEAR;
     opts->threads = 8;
+    opts->kernel = RT_KERNEL_MEGA;
 }
 
 // Chunk layout of the canonical accumulation order.  At least 2^22 jobs

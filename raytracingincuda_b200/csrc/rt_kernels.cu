@@ -368,6 +368,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     }
 }
 
+}  // namespace rt
+
+#include "rt_wavefront.cuh"
+
+namespace rt {
+
 // ------------------------------------------------------------------------------------------
 // out[p] = gamma(scale * sum_c partial[c][p]); 4 pixels per thread, 16-byte stores.
 template <typename T>
@@ -469,6 +475,9 @@ struct rt_ctx {
     BvhView bvh{};
     void *bvh_mem[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // nodes, geom, slot, big_geom, big_slot
     float bvh_build_ms = 0.f;
+    // wavefront variant: path pool
+    void *wf_mem = nullptr;
+    size_t wf_bytes = 0;
 };
 
 constexpr int QUEUE_WORDS = 8;
@@ -669,10 +678,94 @@ template <typename T, int ACCEL> int launch_shape(rt_ctx *ctx, size_t smem, int 
     return RT_OK;
 }
 
+// Wavefront variant: same jobs, same partial planes, two kernels per loop turn over a global pool.
+template <typename T, typename Cam> struct WavefrontImpl {
+    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, int, typename Num<T>::vec4 *) { return RT_EPRECISION; }
+};
+template <typename Cam> struct WavefrontImpl<float, Cam> {
+    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, float4 *partial) {
+        const size_t smem_hit = trace_smem(ctx->blob), smem_shade = ctx->blob.bytes;
+        if (smem_hit > 227 * 1024 || ctx->blob.n > 65535) return RT_EINVAL;
+        TraceArgs<float> A;
+        A.bvh = BvhView{};
+        A.cam = to_dev<float>(cam);
+        A.scene = ctx->blob;
+        A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
+        A.spp = cam.spp; A.max_depth = cam.max_depth;
+        A.width = cam.width;
+        A.tile_rows = o.tile_rows; A.rank = o.rank;
+        A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
+        A.chunks = chunks; A.c_begin = c0;
+        A.pix_local = (unsigned long long)rows_local * cam.width;
+        A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
+        A.partial = partial;
+        A.queue = ctx->queue;
+        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
+        if (A.total_jobs == 0) return RT_OK;
+        // pool: 8 slots per resident thread of the megakernel's shape keeps the state near L2 size
+        const unsigned long long want = (unsigned long long)ctx->sm_count * 2048ull * 4ull;
+        const int n = (int)std::min<unsigned long long>(want, (A.total_jobs + 255ull) & ~255ull);
+        const size_t words = 21;                                   // 4-byte arrays (job is 8 bytes = 2 words)
+        const size_t bytes = (size_t)n * 4 * (words + 2 + 2 * WF_CLASSES) + 256;
+        int rc = ensure(&ctx->wf_mem, &ctx->wf_bytes, bytes);
+        if (rc) return rc;
+        char *base = static_cast<char *>(ctx->wf_mem);
+        auto take = [&](size_t elems, size_t elem_size) { void *p = base; base += ((elems * elem_size + 15) & ~(size_t)15); return p; };
+        WfPool P;
+        P.n = n;
+        float **fl[] = {&P.ox, &P.oy, &P.oz, &P.dx, &P.dy, &P.dz, &P.ax, &P.ay, &P.az, &P.puy, &P.accr, &P.accg, &P.accb, &P.hit_t};
+        for (float **f : fl) *f = static_cast<float *>(take((size_t)n, 4));
+        int **in[] = {&P.hit_id, &P.sample, &P.sample_end, &P.depth, &P.state};
+        for (int **f : in) *f = static_cast<int *>(take((size_t)n, 4));
+        P.pixel = static_cast<uint32_t *>(take((size_t)n, 4));
+        P.job = static_cast<unsigned long long *>(take((size_t)n, 8));
+        int *lists[2] = {static_cast<int *>(take((size_t)n * WF_CLASSES, 4)), static_cast<int *>(take((size_t)n * WF_CLASSES, 4))};
+        unsigned int *counts = static_cast<unsigned int *>(take(16, 4));     // [2][4] counts, then alive
+        unsigned int *cnt[2] = {counts, counts + WF_CLASSES};
+        P.alive = counts + 2 * WF_CLASSES;
+        P.list_in = lists[0]; P.list_out = lists[1];
+        P.count_in = cnt[0]; P.count_out = cnt[1];
+        RT_CUDA(cudaFuncSetAttribute(wf_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
+        RT_CUDA(cudaFuncSetAttribute(wf_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hit));
+        const int gb = (n + 255) / 256, gs = (n + 32 * WF_CLASSES + 255) / 256;
+        wf_init<<<gb, 256, 0, ctx->stream>>>(P);
+        cudaFuncAttributes fa;
+        RT_CUDA(cudaFuncGetAttributes(&fa, wf_intersect));
+        ctx->stats.regs = fa.numRegs; ctx->stats.smem_bytes = (int)smem_hit; ctx->stats.grid = gb; ctx->stats.block = 256;
+        ctx->stats.launches += 1;
+        int cur = 0;
+        for (;;) {
+            const int batch = 16;
+            for (int it = 0; it < batch; ++it) {
+                P.list_in = lists[cur]; P.list_out = lists[cur ^ 1];
+                P.count_in = cnt[cur]; P.count_out = cnt[cur ^ 1];
+                wf_shade<<<gs, 256, smem_shade, ctx->stream>>>(A, P);
+                RT_CUDA(cudaMemsetAsync(P.count_out, 0, WF_CLASSES * sizeof(unsigned int), ctx->stream));
+                RT_CUDA(cudaMemsetAsync(P.alive, 0, sizeof(unsigned int), ctx->stream));
+                wf_intersect<<<gb, 256, smem_hit, ctx->stream>>>(A, P);
+                cur ^= 1;
+                ctx->stats.launches += 2;
+            }
+            RT_CUDA(cudaGetLastError());
+            unsigned int alive = 0;
+            RT_CUDA(cudaMemcpyAsync(&alive, P.alive, sizeof alive, cudaMemcpyDeviceToHost, ctx->stream));
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (alive == 0) break;
+        }
+        return RT_OK;
+    }
+};
+template <typename T, typename Cam>
+int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
+                    typename Num<T>::vec4 *partial) {
+    return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
+}
+
 // Launches the path tracer for chunks [c0,c1) over `rows_local` rows into `partial`.
 template <typename T, typename Cam>
 int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
           typename Num<T>::vec4 *partial) {
+    if (o.kernel == RT_KERNEL_WAVEFRONT) return trace_wavefront<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
     const bool lbvh = (o.accel == RT_ACCEL_LBVH);
     if (lbvh && sizeof(T) != 4) return RT_EPRECISION;
     const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
@@ -724,6 +817,8 @@ int check_opts(const rt_opts &o) {
     if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
     if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH) return RT_EINVAL;
+    if (o.kernel != RT_KERNEL_MEGA && o.kernel != RT_KERNEL_WAVEFRONT) return RT_EINVAL;
+    if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel != RT_ACCEL_LINEAR) return RT_EINVAL;
     return RT_OK;
 }
 
@@ -879,6 +974,7 @@ int rt_destroy(rt_ctx *ctx) {
     if (ctx->frame) cudaFree(ctx->frame);
     if (ctx->queue) cudaFree(ctx->queue);
     for (void *m : ctx->bvh_mem) if (m) cudaFree(m);
+    if (ctx->wf_mem) cudaFree(ctx->wf_mem);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -4,7 +4,7 @@
 // Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
 // setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
 // (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
-// (--seed, --precision, --gpus, --accel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
+// (--seed, --precision, --gpus, --accel, --kernel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
 // behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
 // (global_float_benchmark.sh:53-74) stays valid.
 #include "rt_b200.h"
@@ -50,7 +50,7 @@ struct Args {
     int scene_id = 0, width = 320, height = 192, samples = 10, bounces = 25, threads = 8;
     // extensions
     unsigned long long seed = 1227;
-    bool use_double = false, no_ppm = false, stats = false, lbvh = false;
+    bool use_double = false, no_ppm = false, stats = false, lbvh = false, wavefront = false;
     int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix;
 };
@@ -79,7 +79,7 @@ Args parse(int argc, char **argv) {
         if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
         const bool flag_only = (name == "no-ppm" || name == "stats");
         static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
-                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half"};
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel"};
         bool ok = false;
         for (const char *n : known) ok = ok || name == n;
         if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
@@ -99,6 +99,7 @@ Args parse(int argc, char **argv) {
         else if (name == "split") a.split = value;
         else if (name == "prefix") a.prefix = value;
         else if (name == "accel") a.lbvh = (value == "lbvh");
+        else if (name == "kernel") a.wavefront = (value == "wavefront");
         else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; }
         else if (name == "no-ppm") a.no_ppm = true;
         else if (name == "stats") a.stats = true;
@@ -186,6 +187,7 @@ int main(int argc, char **argv) {
             o.seed = a.seed;
             o.threads = a.threads;
             o.accel = a.lbvh ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
+            o.kernel = a.wavefront ? RT_KERNEL_WAVEFRONT : RT_KERNEL_MEGA;
             if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
             d.rows.resize(static_cast<size_t>(nrows));
