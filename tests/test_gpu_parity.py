@@ -327,3 +327,22 @@ def test_wavefront_row_split(renderer):
         o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=2, tile_rows=4, kernel=api.KERNEL_WAVEFRONT)
         out[rt.partition_rows(50, 4, rank, 2)] = renderer.render(cam, o)
     assert np.array_equal(bits(out), bits(whole))
+
+
+def test_bench_line_schema():
+    """bench.py prints one JSON line with the contract's keys (tiny workload)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "cfg1", "--steps", "2", "--warmup", "3",
+                        "--no-cpu-baseline", "--no-ref-gpu"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert line["metric"] == "Mpath-samples/s" and line["value"] > 0 and line["gpu_launches"] == 4
+    assert line["e2e"]["h2d_bytes_per_step"] == 488 * 40 and line["e2e"]["d2h_bytes_per_step"] == 320 * 192 * 12
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert "workload" in line["config"]
