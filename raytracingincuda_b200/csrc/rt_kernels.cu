@@ -25,6 +25,9 @@ namespace rt {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TRACE_BLOCK = 256;
+#ifndef BVH_STEPS_PER_TURN
+#define BVH_STEPS_PER_TURN 32
+#endif
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 2
 #endif
@@ -244,6 +247,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         sc = view_of<T>(A.scene.base, A.scene);
     }
     unsigned int n_nodes = 0, n_tests = 0;
+    constexpr bool LB = (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4);
+    BvhTrav tv;                                   // LBVH only: resumable traversal (stack in local memory)
+    tv.node = -1;
 
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
@@ -308,13 +314,17 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         }
         if (__all_sync(FULL, state == DEAD)) break;
 
+        // LBVH: a lane whose traversal is still in flight skips shading/regeneration this turn
+        const bool idle = (tv.node < 0);                                  // always true for the linear scan
+        auto ready = [&]() { return LB ? (idle && state == ACTIVE) : (state == ACTIVE); };
+
         // ---- one Philox block per lane and turn, shared by the two consumers: dimension 0 feeds
         //      the camera ray of a fresh sample, dimension depth+1 the scatter of the pending hit ----
         Philox ph;
         ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, fresh ? 0u : (uint32_t)(depth + 1));
         ph.block(0);
-        if (state == ACTIVE && !fresh) {
-            // shade the hit found by the previous turn's scan
+        if (ready() && !fresh) {
+            // shade the hit found by the previous scan
             const bool alive = scatter(sc, hit, ph, ps);
             if (!alive || ++depth >= A.max_depth) {                       // GF camera.h:117 / :84,127 -> black
                 end_path(T(0), T(0), T(0));
@@ -325,18 +335,34 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             }
         }
         // ---- path regeneration: a finished lane starts its next sample in place ----
-        if (state == ACTIVE && fresh) {
+        if (ready() && fresh) {
             camera_ray(A, pi, pj, ph, ps);
             depth = 0;
             fresh = false;
         }
 
-        // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
-        if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(A.bvh, ps.o, ps.d, n_nodes, n_tests);
-        else hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+        bool landed;                                  // this lane's closest hit became available this turn
+        if constexpr (LB) {
+            // ---- LBVH: start the traversal of the new ray, then a bounded number of node visits for
+            //      every lane with a traversal in flight ----
+            const bool launched = ready();
+            if (launched) bvh_start(A.bvh, ps.o, ps.d, tv, n_tests);
+            const bool flying = launched || (state == ACTIVE && !idle);
+#pragma unroll 1
+            for (int step = 0; step < BVH_STEPS_PER_TURN; ++step) {
+                if (!__any_sync(FULL, tv.node >= 0)) break;
+                if (tv.node >= 0) bvh_step(A.bvh, ps.o, ps.d, tv, n_nodes, n_tests);
+            }
+            landed = flying && tv.node < 0;
+            if (landed) hit = tv.hit;
+        } else {
+            // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
+            hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+            landed = (state == ACTIVE);
+        }
 
         // ---- misses end the path here (no random numbers needed); hits are shaded next turn ----
-        if (state == ACTIVE) {
+        if (landed) {
             ++n_seg;
             if (hit.id < 0) {
                 T sr, sg, sb;

@@ -15,9 +15,10 @@
 // error of up to ~8 ulp of a*|oc|^2, i.e. a sphere behaves as if its radius^2 were
 // r^2 + 16*eps*D^2 for a ray whose origin is D away -- far-away rays see "noisy" hits around small
 // spheres.  Child boxes are therefore inflated per ray by
-//   delta = sqrt(rmin^2 + KEPS*D^2) - rmin + BEPS*D
+//   delta = sqrt(rmin^2 + KEPS*D^2) - rmin
 // where D bounds the distance from the ray origin to the box and rmin is the smallest radius
-// below the child, and nodes are culled against best_t with a relative slack.
+// below the child; the slab comparison itself carries a 1e-5 relative slack for its own rounding
+// and nodes are culled against best_t with a 1e-4 relative slack.
 #pragma once
 #include "rt_device.cuh"
 
@@ -35,7 +36,6 @@ struct BvhView {
 };
 
 constexpr float BVH_KEPS = 16.0f * 5.9604645e-8f;   // 16 * 2^-24
-constexpr float BVH_BEPS = 8.0f * 5.9604645e-8f;
 constexpr int BVH_STACK = 64;
 
 // ------------------------------------------------------------------------------ build ------
@@ -158,7 +158,7 @@ __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, flo
     const float fy = fmaxf(fabsf(ly - o.y), fabsf(hy - o.y));
     const float fz = fmaxf(fabsf(lz - o.z), fabsf(hz - o.z));
     const float D2 = fx * fx + fy * fy + fz * fz;
-    const float delta = (sqrtf(rmin * rmin + BVH_KEPS * D2) - rmin) * 1.001f + BVH_BEPS * sqrtf(D2);
+    const float delta = (sqrtf(rmin * rmin + BVH_KEPS * D2) - rmin) * 1.001f + 1e-7f;
     const float t0x = (lx - delta - o.x) * inv.x, t1x = (hx + delta - o.x) * inv.x;
     const float t0y = (ly - delta - o.y) * inv.y, t1y = (hy + delta - o.y) * inv.y;
     const float t0z = (lz - delta - o.z) * inv.z, t1z = (hz + delta - o.z) * inv.z;
@@ -168,64 +168,88 @@ __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, flo
     return ok ? tn : __int_as_float(0x7f800000);
 }
 
-__device__ __forceinline__ Hit<float> bvh_closest_hit(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d,
-                                                      unsigned &n_nodes, unsigned &n_tests) {
-    using N = Num<float>;
-    const float a = dot3(d, d);
-    Hit<float> hit;
-    hit.t = N::inf();
-    hit.id = -1;
-    for (int b = 0; b < bv.nbig; ++b) bvh_test_sphere(__ldg(bv.big_geom + b), __ldg(bv.big_slot + b), o, d, a, hit);
-    n_tests += bv.nbig;
-    if (bv.m == 0) return hit;
-    if (bv.m == 1) {
-        bvh_test_sphere(__ldg(bv.geom), __ldg(bv.slot), o, d, a, hit);
-        ++n_tests;
-        return hit;
-    }
+// Resumable traversal state of one ray.  The stack lives in local memory (L1 resident) and
+// survives across the turns of the persistent loop, so a warp can interleave "a few traversal
+// steps for everybody" with shading/regeneration of the lanes that finished: the lanes of a warp
+// need very different numbers of node visits (mean 18, tail > 100 for rays grazing the ground),
+// and waiting for the slowest lane left 6 of 32 lanes active in the node loop.
+struct BvhTrav {
+    int node;             // current internal node, -1 = no traversal in flight
+    int sp;
+    float a;
     Vec3<float> inv;
-    inv.x = 1.0f / d.x; inv.y = 1.0f / d.y; inv.z = 1.0f / d.z;
+    Hit<float> hit;
     int stack[BVH_STACK];
     float tstack[BVH_STACK];
-    int sp = 0, node = 0;
-    const float inf = N::inf();
-    for (;;) {
-        ++n_nodes;
-        const float4 q0 = __ldg(bv.nodes + 4 * (size_t)node), q1 = __ldg(bv.nodes + 4 * (size_t)node + 1);
-        const float4 q2 = __ldg(bv.nodes + 4 * (size_t)node + 2), q3 = __ldg(bv.nodes + 4 * (size_t)node + 3);
-        const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-        const float limit = hit.t * 1.0001f + 1e-6f;
-        float tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, inv, limit);
-        float tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, inv, limit);
-        if (tl < inf && left < 0) {
-            bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, a, hit);
-            ++n_tests;
-            tl = inf;
-        }
-        if (tr < inf && right < 0) {
-            bvh_test_sphere(__ldg(bv.geom + ~right), __ldg(bv.slot + ~right), o, d, a, hit);
-            ++n_tests;
-            tr = inf;
-        }
-        if (tl < inf && tr < inf) {
-            const bool left_first = tl <= tr;
-            stack[sp] = left_first ? right : left;
-            tstack[sp] = left_first ? tr : tl;
-            ++sp;
-            node = left_first ? left : right;
-            continue;
-        }
-        if (tl < inf) { node = left; continue; }
-        if (tr < inf) { node = right; continue; }
-        // pop, skipping subtrees the current best hit already rules out
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (tstack[sp] <= hit.t * 1.0001f + 1e-6f) { node = stack[sp]; found = true; break; }
-        }
-        if (!found) break;
+};
+
+__device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv,
+                                          unsigned &n_tests) {
+    using N = Num<float>;
+    tv.a = dot3(d, d);
+    tv.hit.t = N::inf();
+    tv.hit.id = -1;
+    for (int b = 0; b < bv.nbig; ++b) bvh_test_sphere(__ldg(bv.big_geom + b), __ldg(bv.big_slot + b), o, d, tv.a, tv.hit);
+    n_tests += bv.nbig;
+    tv.node = -1;
+    tv.sp = 0;
+    if (bv.m == 0) return;
+    if (bv.m == 1) {
+        bvh_test_sphere(__ldg(bv.geom), __ldg(bv.slot), o, d, tv.a, tv.hit);
+        ++n_tests;
+        return;
     }
-    return hit;
+    tv.inv.x = 1.0f / d.x; tv.inv.y = 1.0f / d.y; tv.inv.z = 1.0f / d.z;
+    tv.node = 0;
+}
+
+// one node visit; sets tv.node = -1 when the traversal is complete
+__device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv,
+                                         unsigned &n_nodes, unsigned &n_tests) {
+    const float inf = Num<float>::inf();
+    ++n_nodes;
+    const int node = tv.node;
+    const float4 q0 = __ldg(bv.nodes + 4 * (size_t)node), q1 = __ldg(bv.nodes + 4 * (size_t)node + 1);
+    const float4 q2 = __ldg(bv.nodes + 4 * (size_t)node + 2), q3 = __ldg(bv.nodes + 4 * (size_t)node + 3);
+    const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
+    const float limit = tv.hit.t * 1.0001f + 1e-6f;
+    float tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, tv.inv, limit);
+    float tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, tv.inv, limit);
+    if (tl < inf && left < 0) {
+        bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, tv.a, tv.hit);
+        ++n_tests;
+        tl = inf;
+    }
+    if (tr < inf && right < 0) {
+        bvh_test_sphere(__ldg(bv.geom + ~right), __ldg(bv.slot + ~right), o, d, tv.a, tv.hit);
+        ++n_tests;
+        tr = inf;
+    }
+    if (tl < inf && tr < inf) {
+        const bool left_first = tl <= tr;
+        tv.stack[tv.sp] = left_first ? right : left;
+        tv.tstack[tv.sp] = left_first ? tr : tl;
+        ++tv.sp;
+        tv.node = left_first ? left : right;
+        return;
+    }
+    if (tl < inf) { tv.node = left; return; }
+    if (tr < inf) { tv.node = right; return; }
+    // pop, skipping subtrees the current best hit already rules out
+    tv.node = -1;
+    while (tv.sp > 0) {
+        --tv.sp;
+        if (tv.tstack[tv.sp] <= tv.hit.t * 1.0001f + 1e-6f) { tv.node = tv.stack[tv.sp]; break; }
+    }
+}
+
+// whole traversal in one go (primary pass)
+__device__ __forceinline__ Hit<float> bvh_closest_hit(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d,
+                                                      unsigned &n_nodes, unsigned &n_tests) {
+    BvhTrav tv;
+    bvh_start(bv, o, d, tv, n_tests);
+    while (tv.node >= 0) bvh_step(bv, o, d, tv, n_nodes, n_tests);
+    return tv.hit;
 }
 
 }  // namespace rt
