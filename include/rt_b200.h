@@ -79,7 +79,7 @@ typedef struct rt_camera64 {
 } rt_camera64;
 
 enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
-enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1 };
+enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2 };   /* AUTO: LBVH for float scenes with >= 256 slots */
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 
 /* Per-call options.  Zero-initialise, then set what you need (rt_opts_default does that). */

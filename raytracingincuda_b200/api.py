@@ -180,7 +180,7 @@ def ppm_quantise(rgb):
     return out
 
 
-ACCEL_LINEAR, ACCEL_LBVH = 0, 1
+ACCEL_LINEAR, ACCEL_LBVH, ACCEL_AUTO = 0, 1, 2
 KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
 
 

@@ -792,7 +792,7 @@ template <typename T, typename Cam>
 int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
           typename Num<T>::vec4 *partial) {
     if (o.kernel == RT_KERNEL_WAVEFRONT) return trace_wavefront<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
-    const bool lbvh = (o.accel == RT_ACCEL_LBVH);
+    const bool lbvh = (resolve_accel(ctx, o.accel) == RT_ACCEL_LBVH);
     if (lbvh && sizeof(T) != 4) return RT_EPRECISION;
     const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
     if (smem > 227 * 1024 || (!lbvh && ctx->blob.n > 65535)) return RT_EINVAL;   // too large for the shared-memory scan: use RT_ACCEL_LBVH
@@ -838,13 +838,19 @@ int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsi
     return RT_OK;
 }
 
+// RT_ACCEL_AUTO -> the faster structure for this scene (same image either way)
+int resolve_accel(const rt_ctx *ctx, int accel) {
+    if (accel != RT_ACCEL_AUTO) return accel;
+    return (ctx->scene_prec == 4 && ctx->blob.n >= 256) ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
+}
+
 int check_opts(const rt_opts &o) {
     if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return RT_EINVAL;
     if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
-    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH) return RT_EINVAL;
+    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO) return RT_EINVAL;
     if (o.kernel != RT_KERNEL_MEGA && o.kernel != RT_KERNEL_WAVEFRONT) return RT_EINVAL;
-    if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel != RT_ACCEL_LINEAR) return RT_EINVAL;
+    if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel == RT_ACCEL_LBVH) return RT_EINVAL;
     return RT_OK;
 }
 
@@ -921,7 +927,8 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
 template <typename T, typename Cam>
 int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (!ctx || !cam || !ids || !t) return RT_EINVAL;
-    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH) return RT_EINVAL;
+    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH && accel != RT_ACCEL_AUTO) return RT_EINVAL;
+    if (ctx) accel = resolve_accel(ctx, accel);
     if (accel == RT_ACCEL_LBVH && sizeof(T) != 4) return RT_EPRECISION;
     if (!ctx->scene_dev) return RT_ENOSCENE;
     if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;

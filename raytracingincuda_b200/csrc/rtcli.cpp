@@ -51,6 +51,7 @@ struct Args {
     // extensions
     unsigned long long seed = 1227;
     bool use_double = false, no_ppm = false, stats = false, lbvh = false, wavefront = false;
+    int accel = RT_ACCEL_LINEAR;
     int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix;
 };
@@ -98,9 +99,9 @@ Args parse(int argc, char **argv) {
         else if (name == "gpus") a.gpus = to_int(name, value);
         else if (name == "split") a.split = value;
         else if (name == "prefix") a.prefix = value;
-        else if (name == "accel") a.lbvh = (value == "lbvh");
+        else if (name == "accel") { a.lbvh = (value == "lbvh"); a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : RT_ACCEL_LINEAR); }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
-        else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; }
+        else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
         else if (name == "no-ppm") a.no_ppm = true;
         else if (name == "stats") a.stats = true;
     }
@@ -186,7 +187,7 @@ int main(int argc, char **argv) {
             rt_opts_default(&o);
             o.seed = a.seed;
             o.threads = a.threads;
-            o.accel = a.lbvh ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
+            o.accel = a.accel;
             o.kernel = a.wavefront ? RT_KERNEL_WAVEFRONT : RT_KERNEL_MEGA;
             if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
@@ -246,7 +247,7 @@ int main(int argc, char **argv) {
                      "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d, "
                      "\"accel\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu}\n",
                      mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks,
-                     a.lbvh ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests);
+                     st0.node_visits ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests);
     }
     return 0;
 }
