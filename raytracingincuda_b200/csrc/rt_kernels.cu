@@ -687,6 +687,12 @@ int build_lbvh(rt_ctx *ctx) {
     return RT_OK;
 }
 
+// RT_ACCEL_AUTO -> the faster structure for this scene (same image either way)
+int resolve_accel(const rt_ctx *ctx, int accel) {
+    if (accel != RT_ACCEL_AUTO) return accel;
+    return (ctx->scene_prec == 4 && ctx->blob.n >= 256) ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
+}
+
 size_t trace_smem(const SceneBlob &b) { return (size_t)b.bytes + (size_t)CAND_CAP * TRACE_BLOCK * sizeof(unsigned short); }
 
 template <typename T, int ACCEL> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
@@ -836,12 +842,6 @@ int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsi
     RT_CUDA(cudaGetLastError());
     ctx->stats.launches += 1;
     return RT_OK;
-}
-
-// RT_ACCEL_AUTO -> the faster structure for this scene (same image either way)
-int resolve_accel(const rt_ctx *ctx, int accel) {
-    if (accel != RT_ACCEL_AUTO) return accel;
-    return (ctx->scene_prec == 4 && ctx->blob.n >= 256) ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
 }
 
 int check_opts(const rt_opts &o) {
