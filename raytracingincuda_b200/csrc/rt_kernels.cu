@@ -633,11 +633,29 @@ int build_lbvh(rt_ctx *ctx) {
         RT_CUDA(cudaMemcpyAsync(big_slot, big_idx.data(), sizeof(int) * nbig, cudaMemcpyHostToDevice, st));
         RT_CUDA(cudaStreamSynchronize(st));
     }
+    // device temporaries are released on every exit path
+    struct Scratch {
+        std::vector<void *> ptrs;
+        ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+        cudaError_t get(void **p, size_t bytes) {
+            const cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+            if (e == cudaSuccess) ptrs.push_back(*p);
+            return e;
+        }
+    } tmp;
+    struct Keep {                       // the arrays that outlive the build; freed here only if the build fails
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool armed = true;
+        ~Keep() { if (armed) for (void *q : p) if (q) cudaFree(q); }
+    } keep;
+    keep.p[3] = big_geom; keep.p[4] = big_slot;
     if (m > 0) {
         RT_CUDA(cudaMalloc(&geom_sorted, sizeof(float4) * m));
+        keep.p[1] = geom_sorted;
         RT_CUDA(cudaMalloc(&slot_sorted, sizeof(int) * m));
+        keep.p[2] = slot_sorted;
         RT_CUDA(cudaMalloc(&nodes, sizeof(float4) * 4 * (size_t)std::max(1, m - 1)));
-        // temporaries
+        keep.p[0] = nodes;
         int *small_dev = nullptr, *vals = nullptr, *parent = nullptr, *flags = nullptr;
         uint32_t *keys = nullptr, *keys_sorted = nullptr;
         float *box = nullptr, *rad = nullptr;
@@ -645,15 +663,15 @@ int build_lbvh(rt_ctx *ctx) {
         void *cub_tmp = nullptr;
         size_t cub_bytes = 0;
         const size_t nn = (size_t)2 * m - 1;
-        RT_CUDA(cudaMalloc(&small_dev, sizeof(int) * m));
-        RT_CUDA(cudaMalloc(&vals, sizeof(int) * m));
-        RT_CUDA(cudaMalloc(&keys, sizeof(uint32_t) * m));
-        RT_CUDA(cudaMalloc(&keys_sorted, sizeof(uint32_t) * m));
-        RT_CUDA(cudaMalloc(&box, sizeof(float) * 6 * nn));
-        RT_CUDA(cudaMalloc(&rad, sizeof(float) * nn));
-        RT_CUDA(cudaMalloc(&parent, sizeof(int) * nn));
-        RT_CUDA(cudaMalloc(&flags, sizeof(int) * std::max(1, m - 1)));
-        RT_CUDA(cudaMalloc(&children, sizeof(int2) * std::max(1, m - 1)));
+        RT_CUDA(tmp.get((void **)&small_dev, sizeof(int) * m));
+        RT_CUDA(tmp.get((void **)&vals, sizeof(int) * m));
+        RT_CUDA(tmp.get((void **)&keys, sizeof(uint32_t) * m));
+        RT_CUDA(tmp.get((void **)&keys_sorted, sizeof(uint32_t) * m));
+        RT_CUDA(tmp.get((void **)&box, sizeof(float) * 6 * nn));
+        RT_CUDA(tmp.get((void **)&rad, sizeof(float) * nn));
+        RT_CUDA(tmp.get((void **)&parent, sizeof(int) * nn));
+        RT_CUDA(tmp.get((void **)&flags, sizeof(int) * std::max(1, m - 1)));
+        RT_CUDA(tmp.get((void **)&children, sizeof(int2) * std::max(1, m - 1)));
         RT_CUDA(cudaMemcpyAsync(small_dev, small_idx.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st));
         const int tb = 256, gb = (m + tb - 1) / tb;
         const float3 lo3 = make_float3(lo[0], lo[1], lo[2]);
@@ -661,7 +679,7 @@ int build_lbvh(rt_ctx *ctx) {
                                         hi[2] > lo[2] ? 1.f / (hi[2] - lo[2]) : 0.f);
         bvh_morton_kernel<<<gb, tb, 0, st>>>(geom_dev, small_dev, m, lo3, inv3, keys, vals);
         RT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, vals, slot_sorted, m, 0, 30, st));
-        RT_CUDA(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
+        RT_CUDA(tmp.get(&cub_tmp, cub_bytes));
         RT_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, vals, slot_sorted, m, 0, 30, st));
         bvh_leaves_kernel<<<gb, tb, 0, st>>>(geom_dev, slot_sorted, m, geom_sorted, box, rad);
         if (m > 1) {
@@ -671,13 +689,11 @@ int build_lbvh(rt_ctx *ctx) {
         }
         RT_CUDA(cudaGetLastError());
         RT_CUDA(cudaStreamSynchronize(st));
-        for (void *p : {(void *)small_dev, (void *)vals, (void *)keys, (void *)keys_sorted, (void *)box, (void *)rad,
-                        (void *)parent, (void *)flags, (void *)children, cub_tmp})
-            cudaFree(p);
     }
     RT_CUDA(cudaEventRecord(ctx->ev[2], st));
     RT_CUDA(cudaEventSynchronize(ctx->ev[2]));
     RT_CUDA(cudaEventElapsedTime(&ctx->bvh_build_ms, ctx->ev[3], ctx->ev[2]));
+    keep.armed = false;
     ctx->bvh_mem[0] = nodes; ctx->bvh_mem[1] = geom_sorted; ctx->bvh_mem[2] = slot_sorted;
     ctx->bvh_mem[3] = big_geom; ctx->bvh_mem[4] = big_slot;
     ctx->bvh.nodes = nodes; ctx->bvh.geom = geom_sorted; ctx->bvh.slot = slot_sorted;

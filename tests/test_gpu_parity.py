@@ -346,3 +346,63 @@ def test_bench_line_schema():
     assert line["e2e"]["h2d_bytes_per_step"] == 488 * 40 and line["e2e"]["d2h_bytes_per_step"] == 320 * 192 * 12
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert "workload" in line["config"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_lbvh_random_scenes_equal_linear_scan(renderer, seed):
+    """Random sphere soups (overlaps, radii over 2.5 decades, duplicates, a huge ground sphere):
+    any single differing hit would change the image, so LBVH and linear renders must be bit-equal,
+    and so must the primary (slot id, t) passes."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(200, 2500))
+    s = np.zeros(n, dtype=api.SLOT_DTYPE)
+    spread = float(rng.choice([3.0, 15.0, 60.0]))
+    s["c"] = rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    s["c"][:, 1] = np.abs(s["c"][:, 1]) * 0.3
+    s["r"] = np.exp(rng.uniform(np.log(0.01), np.log(3.0), n)).astype(np.float32)
+    s["type"] = rng.integers(0, 3, n)
+    s["albedo"] = rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32)
+    s["fuzz"] = np.where(s["type"] == 1, rng.uniform(0, 0.5, n), 0).astype(np.float32)
+    s["ri"] = np.where(s["type"] == 2, 1.5, 0).astype(np.float32)
+    s["c"][0] = (0, -1000, 0); s["r"][0] = 1000; s["type"][0] = 0
+    s[n // 2] = s[n // 3]                                       # an exact duplicate: tie on t, lowest slot wins
+    renderer.upload_scene(s)
+    cam = rt.camera(96, 64, 6, 12)
+    ids, t = renderer.primary_hits(cam)
+    bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
+    assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
+    a = renderer.render(cam)
+    seg = renderer.stats().segments
+    b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(a), bits(b))
+    c = renderer.render(cam, api.make_opts(accel=api.ACCEL_AUTO))
+    assert np.array_equal(bits(a), bits(c))
+
+
+def test_cli_end_to_end(tmp_path):
+    """The drop-in binary: stdout is `render_ms,e2e_ms` in the reference's format, the PPM has the
+    reference's naming scheme and its content is the quantised oracle image, byte for byte."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "raytracingincuda_b200", "bin", "b200-raytrace")
+    p = subprocess.run([exe, "--scene_id", "2", "--width", "64", "--height", "40", "--samples", "4", "--bounces", "5",
+                        "--threads", "16", "--stats"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert re.fullmatch(r" {0,14}\d+\.\d{8}, {0,14}\d+\.\d{8}\n", p.stdout), repr(p.stdout)
+    assert len(p.stdout) == 15 + 1 + 15 + 1
+    name = "b200_float_scene2_64x40_4samples_5bounces_16threadsPerBlockRow.ppm"
+    assert os.listdir(tmp_path) == [name]
+    ref, _ = O.render(O.scene(2), O.camera(64, 40, 4, 5))
+    want = tmp_path / "want.ppm"
+    rt.ppm_write(str(want), ref)
+    assert (tmp_path / name).read_bytes() == want.read_bytes()
+    # double precision variant and the prefix override
+    p = subprocess.run([exe, "--scene_id", "3", "--width", "32", "--height", "20", "--samples", "2", "--bounces", "3",
+                        "--precision", "double", "--prefix", "global_double_"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 0 and (tmp_path / "global_double_scene3_32x20_2samples_3bounces_8threadsPerBlockRow.ppm").exists()
+    ref64, _ = O.render(O.scene(3, True), O.camera(32, 20, 2, 3, double=True))
+    got = np.array((tmp_path / "global_double_scene3_32x20_2samples_3bounces_8threadsPerBlockRow.ppm").read_text().split()[4:], dtype=int)
+    x = np.clip(ref64, 0.0, 0.999)
+    assert np.array_equal(got, (256 * x).astype(int).reshape(-1))
