@@ -249,6 +249,24 @@ __device__ __forceinline__ void try_slot(uint32_t geom_addr, int id, const Vec3<
     hit.id = id;
 }
 
+// The reference's loop verbatim (GF hittable.h:86-92): used when a ray has more candidate slots
+// than the per-thread list holds.  Kept out of line: it is cold and the kernel is I-cache sensitive.
+template <typename T>
+__device__ __noinline__ Hit<T> rescan_in_order(uint32_t geom_addr, int n, Vec3<T> o, Vec3<T> d, T a) {
+    using N = Num<T>;
+    constexpr uint32_t REC = sizeof(typename N::vec4);
+    Hit<T> hit;
+    hit.t = N::inf();
+    hit.id = -1;
+    for (int id = 0; id < n; ++id) {
+        const typename N::vec4 s = lds_geom<T>(geom_addr + (uint32_t)id * REC);
+        T h;
+        const T disc = disc_of<T>(s, o, d, a, h);
+        if (!(disc < T(0))) try_slot<T>(geom_addr, id, o, d, a, disc, h, hit);
+    }
+    return hit;
+}
+
 // Appends the slots flagged in `m` (slot k of the word <-> bit 31-k) to the candidate list.
 __device__ __forceinline__ void push_candidates(uint32_t m, int base, unsigned short *cand, int stride, int &count) {
     do {
@@ -307,6 +325,7 @@ __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Ve
     hit.t = N::inf();
     hit.id = -1;
     if (count <= CAND_CAP) {
+#pragma unroll 1
         for (int k = 0; k < count; ++k) {
             const int id = cand[k * stride];
             const typename N::vec4 s = lds_geom<T>(g.addr + (uint32_t)id * REC);
@@ -317,12 +336,7 @@ __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Ve
     } else {
         // more candidate slots than the list holds (never in the reference's scenes): rescan
         // every slot in order, exactly like the reference's loop
-        for (int id = 0; id < n; ++id) {
-            const typename N::vec4 s = lds_geom<T>(g.addr + (uint32_t)id * REC);
-            T h;
-            const T disc = disc_of<T>(s, o, d, a, h);
-            if (!(disc < T(0))) try_slot<T>(g.addr, id, o, d, a, disc, h, hit);
-        }
+        hit = rescan_in_order<T>(g.addr, n, o, d, a);
     }
     return hit;
 }

@@ -48,6 +48,8 @@ template <typename T> struct TraceArgs {
     int chunks, c_begin;               // C and the first chunk of this launch
     unsigned long long pix_local;      // pixels rendered by this launch
     unsigned long long total_jobs;     // (c_end - c_begin) * pix_local
+    unsigned long long magic_pix;      // floor(2^64 / pix_local) + 1: job / pix_local == umul64hi(job, magic_pix)
+    unsigned long long magic_width;    // floor(2^64 / width) + 1
     typename Num<T>::vec4 *partial;    // [job]
     unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests
     BvhView bvh;                       // RT_ACCEL_LBVH only
@@ -295,10 +297,11 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             if (state == NEED_JOB) {
                 job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
                 if (job < A.total_jobs) {
-                    const unsigned long long cl = job / A.pix_local;
+                    // exact divisions by multiply-high (job * pix_local and lp * width stay far below 2^64)
+                    const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;            // magic 0: divisor 1
                     const unsigned long long lp = job - cl * A.pix_local;
                     const int c = A.c_begin + (int)cl;
-                    const int lr = (int)(lp / (unsigned long long)A.width);
+                    const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
                     pi = (int)(lp - (unsigned long long)lr * A.width);
                     pj = global_row(A, lr);
                     pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
@@ -835,6 +838,8 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     A.chunks = chunks; A.c_begin = c0;
     A.pix_local = (unsigned long long)rows_local * cam.width;
     A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
+    A.magic_pix = A.pix_local > 1 ? ~0ull / A.pix_local + 1ull : 0ull;       // 0 encodes "divide by 1"
+    A.magic_width = cam.width > 1 ? ~0ull / (unsigned long long)cam.width + 1ull : 0ull;
     A.partial = partial;
     A.queue = ctx->queue;
     RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
