@@ -92,7 +92,10 @@ typedef struct rt_opts {
     int32_t threads;      /* the reference's --threads; accepted and ignored by the persistent kernel */
     int32_t kernel;       /* RT_KERNEL_*: persistent megakernel (default) or the material-sorted wavefront
                            * variant (float, linear scan); both produce the same image bit for bit */
-    int32_t reserved[7];
+    int32_t place_rows;   /* RT_SPLIT_ROWS only: out_rgb is the FULL frame (width*height*3, device memory -- may be a
+                           * peer GPU's, see rt_enable_peer_access) and this rank's rows are stored at their global
+                           * positions: the row gather becomes direct stores over NVLink, no separate copy */
+    int32_t reserved[6];
 } rt_opts;
 
 typedef struct rt_stats {
@@ -188,6 +191,13 @@ int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double 
 int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t);
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
+
+/* Single-process multi-GPU helpers (the CLI's --gpus N): a frame buffer on this context's device that
+ * other contexts render into with rt_opts.place_rows, after enabling peer (NVLink P2P) access. */
+int rt_frame_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr);
+int rt_frame_free(rt_ctx *ctx, void *dev_ptr);
+int rt_frame_read(rt_ctx *ctx, const void *dev_ptr, void *host_ptr, size_t bytes);
+int rt_enable_peer_access(rt_ctx *ctx, int peer_device);     /* 0 also when access was already enabled */
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,7 @@ class Camera64(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("split", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("tile_rows", C.c_int32), ("accel", C.c_int32), ("threads", C.c_int32), ("kernel", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("place_rows", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Stats(C.Structure):
@@ -89,6 +89,10 @@ SYMBOLS = {
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "rt_get_stats": (C.c_int, [_P, _P]),
+    "rt_frame_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "rt_frame_free": (C.c_int, [_P, _P]),
+    "rt_frame_read": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "rt_enable_peer_access": (C.c_int, [_P, C.c_int]),
 }
 
 _LIB = None
@@ -250,7 +254,7 @@ class Renderer:
         opts = opts or make_opts()
         double = isinstance(cam, Camera64)
         rows = cam.height
-        if opts.split == SPLIT_ROWS:
+        if opts.split == SPLIT_ROWS and not opts.place_rows:
             rows = lib().rt_partition_rows(cam.height, opts.tile_rows, opts.rank, opts.world, None, 0)
         if out is None:
             out = np.empty((rows, cam.width, 3), dtype=np.float64 if double else np.float32)

@@ -405,9 +405,19 @@ namespace rt {
 
 // ------------------------------------------------------------------------------------------
 // out[p] = gamma(scale * sum_c partial[c][p]); 4 pixels per thread, 16-byte stores.
+struct RowPlacement { int width, tile_rows, rank, world; };    // world == 1: rows stay where they are
+
+__device__ __forceinline__ unsigned long long placed_pixel(const RowPlacement &rp, unsigned long long p) {
+    if (rp.world == 1) return p;
+    const int lr = (int)(p / (unsigned long long)rp.width), col = (int)(p - (unsigned long long)lr * rp.width);
+    const int tile = lr / rp.tile_rows, within = lr - tile * rp.tile_rows;
+    return (unsigned long long)((tile * rp.world + rp.rank) * rp.tile_rows + within) * rp.width + col;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) finalize_kernel(const typename Num<T>::vec4 *__restrict__ partial, int chunks,
-                                                       unsigned long long pix, T scale, T *__restrict__ out) {
+                                                       unsigned long long pix, T scale, T *__restrict__ out,
+                                                       const RowPlacement rp) {
     using N = Num<T>;
     const unsigned long long quad = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long p0 = quad * 4ull;
@@ -429,7 +439,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const typename Num<T>::ve
         }
         v[3 * k] = r; v[3 * k + 1] = g; v[3 * k + 2] = b;
     }
-    T *dst = out + p0 * 3ull;
+    // row placement (multi-GPU direct stores into the full frame): a group of 4 pixels stays inside one
+    // row when the width is a multiple of 4, otherwise fall back to per-pixel stores
+    if (rp.world > 1 && (rp.width & 3)) {
+        for (int k = 0; k < cnt; ++k) {
+            T *d1 = out + placed_pixel(rp, p0 + k) * 3ull;
+            d1[0] = v[3 * k]; d1[1] = v[3 * k + 1]; d1[2] = v[3 * k + 2];
+        }
+        return;
+    }
+    T *dst = out + placed_pixel(rp, p0) * 3ull;
     if (cnt == 4 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         constexpr int per = 16 / sizeof(T);
         uint4 *d4 = reinterpret_cast<uint4 *>(dst);
@@ -862,11 +881,12 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
 }
 
 template <typename T>
-int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsigned long long pix, T scale, T *out_dev) {
+int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsigned long long pix, T scale, T *out_dev,
+             RowPlacement rp = RowPlacement{0, 1, 0, 1}) {
     if (pix == 0) return RT_OK;
     const unsigned long long quads = (pix + 3) / 4;
     const unsigned grid = (unsigned)((quads + 255) / 256);
-    finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(partial, chunks, pix, scale, out_dev);
+    finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(partial, chunks, pix, scale, out_dev, rp);
     RT_CUDA(cudaGetLastError());
     ctx->stats.launches += 1;
     return RT_OK;
@@ -918,6 +938,10 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
     ctx->stats = rt_stats{};
     const size_t out_bytes = (size_t)pix * 3 * sizeof(T);
     const bool out_on_device = is_device_ptr(out_rgb);
+    const bool place = o.split == RT_SPLIT_ROWS && o.place_rows != 0;
+    if (place && !out_on_device) return RT_EINVAL;                   // direct row placement needs a device frame
+    RowPlacement rp{cam->width, 1, 0, 1};
+    if (place) rp = RowPlacement{cam->width, o.tile_rows, o.rank, o.world};
     T *frame = out_rgb;
     if (!out_on_device) {
         rc = ensure(&ctx->frame, &ctx->frame_bytes, out_bytes ? out_bytes : 16);
@@ -925,6 +949,7 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
         frame = static_cast<T *>(ctx->frame);
     }
     RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (cam->max_depth <= 0 && place) return RT_EINVAL;
     if (cam->max_depth <= 0) {
         // GF camera.h:84,127: no bounce budget -> every path is black
         RT_CUDA(cudaMemsetAsync(frame, 0, out_bytes, ctx->stream));
@@ -936,7 +961,7 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
         rc = trace<T>(ctx, *cam, o, rows_local, chunks, 0, chunks, static_cast<V4 *>(ctx->partial));
         if (rc) return rc;
         RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        rc = finalize<T>(ctx, static_cast<const V4 *>(ctx->partial), chunks, pix, static_cast<T>(cam->scale), frame);
+        rc = finalize<T>(ctx, static_cast<const V4 *>(ctx->partial), chunks, pix, static_cast<T>(cam->scale), frame, rp);
         if (rc) return rc;
     }
     RT_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1123,6 +1148,36 @@ int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double 
 }
 int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t) {
     return primary_impl<float>(ctx, cam, accel, ids, t);
+}
+
+int rt_frame_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr) {
+    if (!ctx || !dev_ptr || bytes == 0) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMalloc(dev_ptr, bytes));
+    return RT_OK;
+}
+int rt_frame_free(rt_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaFree(dev_ptr));
+    return RT_OK;
+}
+int rt_frame_read(rt_ctx *ctx, const void *dev_ptr, void *host_ptr, size_t bytes) {
+    if (!ctx || !dev_ptr || !host_ptr) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMemcpy(host_ptr, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+int rt_enable_peer_access(rt_ctx *ctx, int peer_device) {
+    if (!ctx) return RT_EINVAL;
+    if (peer_device == ctx->device) return RT_OK;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    int can = 0;
+    RT_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return RT_ENODEVICE;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RT_OK; }
+    return e == cudaSuccess ? RT_OK : (int)e;
 }
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats) {

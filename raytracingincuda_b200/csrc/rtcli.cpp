@@ -4,7 +4,7 @@
 // Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
 // setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
 // (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
-// (--seed, --precision, --gpus, --accel, --kernel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
+// (--seed, --precision, --gpus, --gather, --accel, --kernel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
 // behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
 // (global_float_benchmark.sh:53-74) stays valid.
 #include "rt_b200.h"
@@ -53,7 +53,7 @@ struct Args {
     bool use_double = false, no_ppm = false, stats = false, lbvh = false, wavefront = false;
     int accel = RT_ACCEL_LINEAR;
     int gpus = 1, scaled_half = 0;
-    std::string split = "rows", prefix;
+    std::string split = "rows", prefix, gather = "p2p";
 };
 
 int to_int(const std::string &name, const std::string &text) {
@@ -80,7 +80,7 @@ Args parse(int argc, char **argv) {
         if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
         const bool flag_only = (name == "no-ppm" || name == "stats");
         static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
-                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel"};
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel", "gather"};
         bool ok = false;
         for (const char *n : known) ok = ok || name == n;
         if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
@@ -99,6 +99,7 @@ Args parse(int argc, char **argv) {
         else if (name == "gpus") a.gpus = to_int(name, value);
         else if (name == "split") a.split = value;
         else if (name == "prefix") a.prefix = value;
+        else if (name == "gather") a.gather = value;
         else if (name == "accel") { a.lbvh = (value == "lbvh"); a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : RT_ACCEL_LINEAR); }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
         else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
@@ -177,7 +178,17 @@ int main(int argc, char **argv) {
     CHECK(rt_camera_init(&cam, W, H, a.samples, a.bounces));
     CHECK(rt_camera_init64(&cam64, W, H, a.samples, a.bounces));
 
-    // render (GF main.cu:326-341): one host thread per device, interleaved row tiles
+    // render (GF main.cu:326-341): one host thread per device, rows interleaved across devices.
+    // With more than one device the frame lives on device 0 and every device stores its finished rows
+    // straight into it over NVLink P2P (rt_opts.place_rows); if peer access is not available the rows go
+    // through host memory instead.
+    const size_t frame_bytes = npix * 3 * (a.use_double ? sizeof(double) : sizeof(float));
+    void *frame_dev = nullptr;
+    bool p2p = a.gpus > 1 && a.gather != "host";
+    if (p2p) {
+        for (int g = 1; g < a.gpus && p2p; ++g) p2p = rt_enable_peer_access(dev[g].ctx, 0) == RT_OK;
+        if (p2p) CHECK(rt_frame_alloc(dev[0].ctx, frame_bytes, &frame_dev));
+    }
     std::vector<std::thread> workers;
     std::vector<int> rcs(static_cast<size_t>(a.gpus), RT_OK);
     for (int g = 0; g < a.gpus; ++g) {
@@ -189,15 +200,17 @@ int main(int argc, char **argv) {
             o.threads = a.threads;
             o.accel = a.accel;
             o.kernel = a.wavefront ? RT_KERNEL_WAVEFRONT : RT_KERNEL_MEGA;
-            if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; }
+            if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; o.place_rows = p2p ? 1 : 0; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
             d.rows.resize(static_cast<size_t>(nrows));
             if (a.gpus > 1) rt_partition_rows(H, o.tile_rows, g, a.gpus, d.rows.data(), nrows);
             if (a.use_double) {
-                double *dst = a.gpus > 1 ? (d.rgb64.resize(static_cast<size_t>(nrows) * W * 3), d.rgb64.data()) : frame64.data();
+                double *dst = p2p ? static_cast<double *>(frame_dev)
+                                  : (a.gpus > 1 ? (d.rgb64.resize(static_cast<size_t>(nrows) * W * 3), d.rgb64.data()) : frame64.data());
                 rcs[g] = rt_render64(d.ctx, &cam64, &o, dst, &d.render_ms);
             } else {
-                float *dst = a.gpus > 1 ? (d.rgb.resize(static_cast<size_t>(nrows) * W * 3), d.rgb.data()) : frame.data();
+                float *dst = p2p ? static_cast<float *>(frame_dev)
+                                 : (a.gpus > 1 ? (d.rgb.resize(static_cast<size_t>(nrows) * W * 3), d.rgb.data()) : frame.data());
                 rcs[g] = rt_render(d.ctx, &cam, &o, dst, &d.render_ms);
             }
             rt_get_stats(d.ctx, &d.stats);
@@ -207,7 +220,11 @@ int main(int argc, char **argv) {
     for (int g = 0; g < a.gpus; ++g) CHECK(rcs[g]);
     float render_ms = 0.f;
     for (const auto &d : dev) render_ms = d.render_ms > render_ms ? d.render_ms : render_ms;   // max over devices
-    if (a.gpus > 1) {
+    if (p2p) {
+        CHECK(rt_frame_read(dev[0].ctx, frame_dev, a.use_double ? static_cast<void *>(frame64.data()) : static_cast<void *>(frame.data()),
+                            frame_bytes));
+        CHECK(rt_frame_free(dev[0].ctx, frame_dev));
+    } else if (a.gpus > 1) {
         for (const auto &d : dev)
             for (size_t r = 0; r < d.rows.size(); ++r) {
                 const size_t dst = static_cast<size_t>(d.rows[r]) * W * 3, src = r * W * 3;

@@ -406,3 +406,24 @@ def test_cli_end_to_end(tmp_path):
     got = np.array((tmp_path / "global_double_scene3_32x20_2samples_3bounces_8threadsPerBlockRow.ppm").read_text().split()[4:], dtype=int)
     x = np.clip(ref64, 0.0, 0.999)
     assert np.array_equal(got, (256 * x).astype(int).reshape(-1))
+
+
+@pytest.mark.parametrize("w,h", [(96, 70), (50, 33)])
+def test_place_rows_writes_the_full_frame_in_place(renderer, w, h):
+    """rt_opts.place_rows: each rank stores its rows at their global positions of one device frame
+    (what the CLI does across GPUs over NVLink P2P); width % 4 != 0 takes the per-pixel store path."""
+    import torch
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(w, h, 6, 10)
+    whole = renderer.render(cam)
+    frame = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+    for rank in range(3):
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=3, tile_rows=2)
+        o.place_rows = 1
+        renderer.render(cam, o, out=frame)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(frame.cpu().numpy()), bits(whole))
+    with pytest.raises(rt.RtError):
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=0, world=2)
+        o.place_rows = 1
+        renderer.render(cam, o, out=np.zeros((h, w, 3), dtype=np.float32))     # host frame: rejected
