@@ -56,7 +56,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--split", default="rows", choices=["rows", "spp"])
+    ap.add_argument("--spp-combine", default="gather", choices=["gather", "reduce"],
+                    help="spp split: ordered gather (bit-exact) or NCCL sum-reduce of the accumulation buffer")
     ap.add_argument("--tile-rows", type=int, default=1)
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "ipc"],
+                    help="rows split: NCCL gather to rank 0, or direct P2P stores into rank 0's frame (CUDA IPC)")
     ap.add_argument("--accel", default="linear", choices=["linear", "lbvh"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -255,6 +259,11 @@ def main():
         torch.cuda.synchronize()
 
     frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device=device) if rank == 0 else None
+    frame_alias = None
+    if world > 1 and args.split == "rows" and args.gather == "ipc":
+        frame_alias = rtdist.share_from_rank0(frame_dev, rank, world)     # rank 0's frame, mapped into every process
+        if rank != 0:
+            r.enable_peer_access(0)
     trace_ms, launches, segs, tests, nodes = [], [0], [0], [0], [0]
 
     def note_stats():
@@ -270,6 +279,13 @@ def main():
             r.render(cam, api.make_opts(accel=accel), out=frame_dev)
             note_stats()
             return frame_dev
+        if args.split == "rows" and frame_alias is not None:
+            def render_into(frame):
+                o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows, accel=accel)
+                o.place_rows = 1
+                r.render(cam, o, out=frame)
+                note_stats()
+            return rtdist.render_rows_placed(render_into, frame_alias, rank, world)
         if args.split == "rows":
             def render_rows(buf):
                 r.render(cam, api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows, accel=accel), out=buf)
@@ -279,8 +295,8 @@ def main():
         def render_partials(planes, c0, c1):
             r.render_partials(cam, api.make_opts(split=api.SPLIT_SPP, rank=rank, world=world, accel=accel), planes)
             note_stats()
-        return rtdist.render_spp_split(render_partials, lambda planes: r.finalize(cam, planes, chunks, out=frame_dev),
-                                       W, H, chunks, rank, world, device)
+        return rtdist.render_spp_split(render_partials, lambda planes: r.finalize(cam, planes, planes.shape[0], out=frame_dev),
+                                       W, H, chunks, rank, world, device, combine=args.spp_combine)
 
     frame_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
 
@@ -369,7 +385,7 @@ def main():
             "config": {"workload": workload_name(args.workload),
                        "implementation": f"float, {'on-GPU LBVH' if lbvh else 'linear scan in shared memory'}",
                        "l2": "inputs regenerate per step; "
-                                   f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": args.split if world > 1 else "none",
+                                   f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else args.gather))) if world > 1 else "none",
                        "chunks": chunks, "seed": 1227},
             "render_ms": round(ms_per_step, 3),
             "e2e": {"value": round(e2e_value, 3), "unit": METRIC, "h2d_bytes_per_step": int(slots.nbytes),

@@ -234,6 +234,9 @@ class Renderer:
     def __exit__(self, *exc):
         self.close()
 
+    def enable_peer_access(self, peer_device):
+        _ck(lib().rt_enable_peer_access(self._ctx, peer_device), "rt_enable_peer_access")
+
     def set_stream(self, cuda_stream):
         _ck(lib().rt_set_stream(self._ctx, _P(cuda_stream)), "rt_set_stream")
 

@@ -54,16 +54,30 @@ def render_rows_split(render_rows, width, height, tile_rows, rank, world, device
     return frame
 
 
-def render_spp_split(render_partials, finalize, width, height, chunks, rank, world, device, group=None):
+def render_spp_split(render_partials, finalize, width, height, chunks, rank, world, device, group=None,
+                     combine="gather"):
     """``render_partials(planes, c0, c1)`` fills ``planes`` ((c1-c0, width*height, 4) float32 on
     ``device``) with this rank's chunk sums; ``finalize(all_planes)`` turns the (chunks, W*H, 4)
-    stack into the frame on rank 0."""
+    stack into the frame on rank 0.
+
+    combine="gather" (default): rank 0 receives every plane and adds them in chunk order --
+    bit-identical to the 1-GPU frame.  combine="reduce": every rank adds its own planes in chunk
+    order and one NCCL sum-reduce of the W*H*4 accumulation buffer delivers the total to rank 0 --
+    1/world of the traffic, but the association order of the cross-rank sum is NCCL's, so the
+    frame can differ from the canonical one in the last ulp."""
     bounds = [api.partition_chunks(chunks, r, world) for r in range(world)]
     c0, c1 = bounds[rank]
     max_c = max(b[1] - b[0] for b in bounds)
     local = torch.zeros((max_c, width * height, 4), dtype=torch.float32, device=device)
     if c1 > c0:
         render_partials(local[:c1 - c0], c0, c1)
+    if combine == "reduce":
+        acc = local[0].clone()
+        for k in range(1, c1 - c0):
+            acc += local[k]
+        if world > 1:
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM, group=group)
+        return finalize(acc.unsqueeze(0).contiguous()) if rank == 0 else None
     parts = _gather_to_rank0(local, rank, world, group)
     if rank != 0:
         return None
@@ -72,3 +86,29 @@ def render_spp_split(render_partials, finalize, width, height, chunks, rank, wor
     else:
         planes = torch.cat([p[:b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)
     return finalize(planes.contiguous())
+
+
+def share_from_rank0(tensor, rank, world, group=None):
+    """CUDA IPC: returns, on every rank, a tensor that aliases rank 0's ``tensor`` (device memory of
+    rank 0's GPU mapped into this process).  With peer access enabled, a rank's kernels can then store
+    straight into rank 0's frame over NVLink (``rt_opts.place_rows``): the row gather needs no collective
+    and no copy.  All GPUs must be visible to every process (the torchrun default)."""
+    if world == 1:
+        return tensor
+    from torch.multiprocessing.reductions import reduce_tensor
+    box = [reduce_tensor(tensor) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    if rank == 0:
+        return tensor
+    rebuild, args = box[0]
+    return rebuild(*args)
+
+
+def render_rows_placed(render_into, frame_alias, rank, world, group=None):
+    """Row split without a gather: ``render_into(frame_alias)`` renders this rank's rows with
+    ``place_rows`` into the shared frame; a barrier makes the frame complete on rank 0."""
+    render_into(frame_alias)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=group)
+    return frame_alias if rank == 0 else None
