@@ -59,8 +59,6 @@ def parse_args():
     ap.add_argument("--spp-combine", default="gather", choices=["gather", "reduce"],
                     help="spp split: ordered gather (bit-exact) or NCCL sum-reduce of the accumulation buffer")
     ap.add_argument("--tile-rows", type=int, default=1)
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "ipc"],
-                    help="rows split: NCCL gather to rank 0, or direct P2P stores into rank 0's frame (CUDA IPC)")
     ap.add_argument("--accel", default="linear", choices=["linear", "lbvh"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -259,11 +257,6 @@ def main():
         torch.cuda.synchronize()
 
     frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device=device) if rank == 0 else None
-    frame_alias = None
-    if world > 1 and args.split == "rows" and args.gather == "ipc":
-        frame_alias = rtdist.share_from_rank0(frame_dev, rank, world)     # rank 0's frame, mapped into every process
-        if rank != 0:
-            r.enable_peer_access(0)
     trace_ms, launches, segs, tests, nodes = [], [0], [0], [0], [0]
 
     def note_stats():
@@ -279,13 +272,6 @@ def main():
             r.render(cam, api.make_opts(accel=accel), out=frame_dev)
             note_stats()
             return frame_dev
-        if args.split == "rows" and frame_alias is not None:
-            def render_into(frame):
-                o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows, accel=accel)
-                o.place_rows = 1
-                r.render(cam, o, out=frame)
-                note_stats()
-            return rtdist.render_rows_placed(render_into, frame_alias, rank, world)
         if args.split == "rows":
             def render_rows(buf):
                 r.render(cam, api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows, accel=accel), out=buf)
@@ -385,7 +371,7 @@ def main():
             "config": {"workload": workload_name(args.workload),
                        "implementation": f"float, {'on-GPU LBVH' if lbvh else 'linear scan in shared memory'}",
                        "l2": "inputs regenerate per step; "
-                                   f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else args.gather))) if world > 1 else "none",
+                                   f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else "nccl-gather"))) if world > 1 else "none",
                        "chunks": chunks, "seed": 1227},
             "render_ms": round(ms_per_step, 3),
             "e2e": {"value": round(e2e_value, 3), "unit": METRIC, "h2d_bytes_per_step": int(slots.nbytes),

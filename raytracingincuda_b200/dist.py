@@ -87,28 +87,3 @@ def render_spp_split(render_partials, finalize, width, height, chunks, rank, wor
         planes = torch.cat([p[:b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)
     return finalize(planes.contiguous())
 
-
-def share_from_rank0(tensor, rank, world, group=None):
-    """CUDA IPC: returns, on every rank, a tensor that aliases rank 0's ``tensor`` (device memory of
-    rank 0's GPU mapped into this process).  With peer access enabled, a rank's kernels can then store
-    straight into rank 0's frame over NVLink (``rt_opts.place_rows``): the row gather needs no collective
-    and no copy.  All GPUs must be visible to every process (the torchrun default)."""
-    if world == 1:
-        return tensor
-    from torch.multiprocessing.reductions import reduce_tensor
-    box = [reduce_tensor(tensor) if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0, group=group)
-    if rank == 0:
-        return tensor
-    rebuild, args = box[0]
-    return rebuild(*args)
-
-
-def render_rows_placed(render_into, frame_alias, rank, world, group=None):
-    """Row split without a gather: ``render_into(frame_alias)`` renders this rank's rows with
-    ``place_rows`` into the shared frame; a barrier makes the frame complete on rank 0."""
-    render_into(frame_alias)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier(group=group)
-    return frame_alias if rank == 0 else None
