@@ -427,3 +427,61 @@ def test_place_rows_writes_the_full_frame_in_place(renderer, w, h):
         o = api.make_opts(split=api.SPLIT_ROWS, rank=0, world=2)
         o.place_rows = 1
         renderer.render(cam, o, out=np.zeros((h, w, 3), dtype=np.float32))     # host frame: rejected
+
+
+def test_config4_frame_size_properties(renderer):
+    """BASELINE config 4's frame (3840x2160) at reduced spp: path/segment accounting, an 8-way row
+    split placed straight into one frame equals the whole-frame render, the LBVH render equals the
+    linear-scan render, and the primary pass agrees between both structures -- all bit for bit."""
+    import torch
+    W, H = 3840, 2160
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(W, H, 4, 50)
+    whole = torch.empty((H, W, 3), dtype=torch.float32, device="cuda:0")
+    renderer.render(cam, out=whole)
+    st = renderer.stats()
+    assert st.paths == W * H * 4 and st.chunks == 4 and 2.0 < st.segments / st.paths < 4.0
+    placed = torch.zeros_like(whole)
+    for rank in range(8):
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=8)
+        o.place_rows = 1
+        renderer.render(cam, o, out=placed)
+    assert torch.equal(placed.view(torch.int32), whole.view(torch.int32))
+    lb = torch.empty_like(whole)
+    renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH), out=lb)
+    assert renderer.stats().segments == st.segments
+    assert torch.equal(lb.view(torch.int32), whole.view(torch.int32))
+    img = whole.cpu().numpy()
+    assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 1.0001
+    ids, t = renderer.primary_hits(rt.camera(W, H))
+    bids, bt = renderer.primary_hits(rt.camera(W, H), accel=api.ACCEL_LBVH)
+    assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
+    assert len(np.unique(ids)) > 300                      # most of the 488 slots are visible at 4K
+
+
+def test_invalid_inputs_fail_loudly(renderer):
+    """Empty scene, bad material type, zero-sized frame, render before upload, precision mismatch."""
+    with pytest.raises(rt.RtError):
+        renderer.upload_scene(np.zeros(0, dtype=api.SLOT_DTYPE))
+    bad = rt.scene(2).copy()
+    bad["type"][3] = 7
+    with pytest.raises(rt.RtError):
+        renderer.upload_scene(bad)
+    fresh = rt.Renderer(0)
+    try:
+        with pytest.raises(rt.RtError) as e:
+            fresh.render(rt.camera(8, 8, 1, 1))
+        assert e.value.code == -2                          # RT_ENOSCENE
+        fresh.upload_scene(rt.scene(2, double=True))
+        with pytest.raises(rt.RtError) as e:
+            fresh.render(rt.camera(8, 8, 1, 1))            # float call on a double scene
+        assert e.value.code == -6                          # RT_EPRECISION
+    finally:
+        fresh.close()
+    renderer.upload_scene(rt.scene(2))
+    cam = rt.camera(8, 8, 1, 1)
+    cam.width = 0
+    with pytest.raises(rt.RtError):
+        renderer.render(cam, out=np.zeros((8, 8, 3), dtype=np.float32))
+    one = renderer.render(rt.camera(1, 1, 1, 1))           # the smallest frame there is
+    assert one.shape == (1, 1, 3) and np.isfinite(one).all()
