@@ -217,11 +217,34 @@ def reference_gpu_kernel():
 
 
 # ------------------------------------------------------------------ B200 arm ----------------
+class QuietStdout:
+    """Route file descriptor 1 to stderr while the run is in progress: libraries (NCCL prints its version
+    banner with printf) must not add lines to the one-JSON-line contract of stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    with QuietStdout():
+        line = run_b200_arm(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_b200_arm(args):
 
     import numpy as np
     import torch
@@ -337,6 +360,7 @@ def main():
     ms, e2e_ms, step_trace_ms = [float(x) for x in t.tolist()]
     segments, sphere_tests, node_visits = [int(x) for x in seg_t.tolist()]
 
+    line = None
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         paths = W * H * spp
@@ -422,10 +446,10 @@ def main():
                 line["reference_gpu_kernel"] = reference_gpu_kernel()
             except Exception as e:  # the comparator is informative, never fatal
                 line["reference_gpu_kernel"] = {"error": str(e)[:200]}
-        print(json.dumps(line))
     r.close()
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -456,7 +456,7 @@ def test_config4_frame_size_properties(renderer):
     ids, t = renderer.primary_hits(rt.camera(W, H))
     bids, bt = renderer.primary_hits(rt.camera(W, H), accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
-    assert len(np.unique(ids)) > 300                      # most of the 488 slots are visible at 4K
+    assert len(np.unique(ids)) > 100                      # the 20-degree view sees about 140 of the 488 slots
 
 
 def test_invalid_inputs_fail_loudly(renderer):
