@@ -52,7 +52,8 @@ template <typename T> struct TraceArgs {
     typename Num<T>::vec4 *partial;    // [job]
     unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests
     BvhView bvh;                       // RT_ACCEL_LBVH only
-    int bvh_steps;                     // node visits per loop turn before finished lanes are shaded
+    int bvh_steps;                     // at most this many node visits per loop turn ...
+    int bvh_min_active;                // ... and the round ends once fewer lanes than this are still traversing
 };
 
 // ------------------------------------------------------------------------------------------
@@ -353,7 +354,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             const bool flying = launched || (state == ACTIVE && !idle);
 #pragma unroll 1
             for (int step = 0; step < A.bvh_steps; ++step) {
-                if (!__any_sync(FULL, tv.node >= 0)) break;
+                // stop early when enough lanes have finished: they are shaded and regenerated together,
+                // and the node loop never runs with a nearly empty warp
+                const int flying_lanes = __popc(__ballot_sync(FULL, tv.node >= 0));
+                if (flying_lanes == 0 || (flying_lanes < A.bvh_min_active && step > 0)) break;
                 if (tv.node >= 0) bvh_step(A.bvh, ps.o, ps.d, tv, n_nodes, n_tests);
             }
             landed = flying && tv.node < 0;
@@ -759,6 +763,7 @@ template <typename Cam> struct WavefrontImpl<float, Cam> {
         TraceArgs<float> A;
         A.bvh = BvhView{};
         A.bvh_steps = 0;
+        A.bvh_min_active = 0;
         A.cam = to_dev<float>(cam);
         A.scene = ctx->blob;
         A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
@@ -853,7 +858,9 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     A.bvh_steps = 8;
     for (int m = ctx->bvh.m; m > 0; m >>= 1) A.bvh_steps += 1;
     if (A.bvh_steps > 32) A.bvh_steps = 32;
-    if (const char *e = getenv("RT_BVH_STEPS")) A.bvh_steps = atoi(e) > 0 ? atoi(e) : A.bvh_steps;   // tuning knob
+    A.bvh_min_active = 0;
+    if (const char *e = getenv("RT_BVH_STEPS")) A.bvh_steps = atoi(e) > 0 ? atoi(e) : A.bvh_steps;   // tuning knobs
+    if (const char *e = getenv("RT_BVH_MIN_ACTIVE")) A.bvh_min_active = atoi(e);
     A.cam = to_dev<T>(cam);
     A.scene = ctx->blob;
     A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
