@@ -99,6 +99,8 @@ struct Philox {
 //   [vec4 matl[n]]       albedo.xyz, param (fuzz for metal, refraction index for dielectric)
 //   [int  type[n4]]
 //   [T    rinv[n]]       1/radius (host IEEE division, the value rcp.rn gives on the device)
+//   [float4 filt[2*half_pad]]  float scenes: centre.xyz, -(|centre|^2 - radius^2) per slot, two halves
+//   [int  far[n_far]]          float scenes: slots kept out of filt[]
 // staged into shared memory by one thread with cp.async.bulk + an mbarrier (TMA bulk copy).
 template <typename T> struct SceneView {
     const typename Num<T>::vec4 *geom;
@@ -113,6 +115,13 @@ struct SceneBlob {
     uint32_t bytes;         // multiple of 16
     uint32_t matl_off, type_off, rinv_off;
     int n;
+    // conservative pre-filter of the float scan (see "paired filter scan" below); filter_ok == 0: exact scan only
+    uint32_t filt_off, far_off;
+    int filter_ok;
+    int n_half;             // slots [0, n_half) live in half 0 of filt[], slots [n_half, n) in half 1
+    int half_pad;           // records per half (n_half rounded up to 8; padding and far slots never pass)
+    int n_far;              // slots excluded from the filter (far from the origin): always tested exactly
+    float bound;            // max over filtered slots of |centre| + radius, rounded up
 };
 
 template <typename T>
@@ -201,7 +210,8 @@ __device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__dou
 // `cand` points at this thread's column of a [CAND_CAP][blockDim.x] uint16 array.
 // After the full blocks a tail of up to three groups of 8 covers n % 32; the geometry array is
 // padded with zero records to a multiple of 8 and `tail_mask` clears the padding's bits.
-constexpr int CAND_CAP = 24;
+constexpr int CAND_CAP = 32;       // exact scan: one list of 32; paired filter scan: two lists of 16 (own ray, neighbour's ray)
+constexpr int PAIR_CAP = CAND_CAP / 2;
 
 template <typename T> struct Hit { T t; int id; };
 
@@ -210,6 +220,10 @@ struct ScanGeom {
     int blocks;           // n / 32 full blocks
     int tail_groups;      // ceil((n % 32) / 8) groups of 8 after the full blocks
     uint32_t tail_mask;   // valid-slot bits of the tail word (slot k of a word <-> bit 31-k)
+    // paired filter scan (float scenes with blob.filter_ok)
+    uint32_t filt_addr, far_addr;
+    int filter_ok, n_half, half_pad, n_far;
+    float bound;
 };
 
 __device__ __forceinline__ ScanGeom scan_geom(uint32_t addr, int n) {
@@ -219,6 +233,22 @@ __device__ __forceinline__ ScanGeom scan_geom(uint32_t addr, int n) {
     const int rem = n & 31;
     g.tail_groups = (rem + 7) >> 3;
     g.tail_mask = rem ? ~(0xffffffffu >> rem) : 0u;
+    g.filt_addr = g.far_addr = 0u;
+    g.filter_ok = g.n_half = g.half_pad = g.n_far = 0;
+    g.bound = 0.0f;
+    return g;
+}
+
+// scan description of a scene blob staged at shared-space address `addr`
+__device__ __forceinline__ ScanGeom scan_geom(uint32_t addr, const SceneBlob &b) {
+    ScanGeom g = scan_geom(addr, b.n);
+    g.filt_addr = addr + b.filt_off;
+    g.far_addr = addr + b.far_off;
+    g.filter_ok = b.filter_ok;
+    g.n_half = b.n_half;
+    g.half_pad = b.half_pad;
+    g.n_far = b.n_far;
+    g.bound = b.bound;
     return g;
 }
 
@@ -282,8 +312,8 @@ __device__ __forceinline__ void push_candidates(uint32_t m, int base, unsigned s
 #endif
 
 template <typename T>
-__device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
-                                              unsigned short *cand, int stride) {
+__device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
+                                                    unsigned short *cand, int stride) {
     using N = Num<T>;
     constexpr uint32_t REC = sizeof(typename N::vec4);
     const T a = dot3(d, d);                                     // GF hittable.h:42
@@ -339,6 +369,162 @@ __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Ve
         hit = rescan_in_order<T>(g.addr, n, o, d, a);
     }
     return hit;
+}
+
+// ------------------------------------------------------------------------------------------
+// Paired filter scan (float scenes).  Same answer as closest_hit_exact, about half the issue slots.
+//
+// (1) Conservative filter.  With d' = d/|d| the reference's discriminant has the sign of
+//         F = (c.d' - o.d')^2 + 2 c.o - (|c|^2 - r^2) - |o|^2          ( = r^2 - dist(centre, ray)^2 )
+//     which needs 7 fused multiply-adds per (ray, sphere) against a per-ray threshold when
+//     nk = -(|c|^2 - r^2) is precomputed per sphere:  h = fma(cx,dx', fma(cy,dy', fma(cz,dz', -o.d')));
+//     t = fma(cx,2ox, fma(cy,2oy, fma(cz,2oz, nk)));  v = fma(h,h,t);  candidate iff v >= |o|^2 - E.
+//     E = 72 * 2^-24 * (|o| + bound)^2 covers BOTH the rounding error of v and the rounding error of
+//     the reference's own float discriminant (derivation: DESIGN.md section 6), so every slot whose
+//     reference discriminant is >= 0 is a candidate; candidates then go through the reference's exact
+//     arithmetic (disc_of, IEEE sqrt/div), which also rejects the filter's false positives.
+//     Spheres far from the origin relative to the rest (the 1000-unit ground sphere) would inflate E for
+//     every slot; they are kept out of filt[] and tested exactly for every ray (blob.far).
+// (2) Two rays per lane.  Lanes 2i and 2i+1 exchange their ray constants; each scans HALF of the
+//     slots for BOTH rays, so one LDS.128 feeds two tests (the LSU return path, not the FMA pipe, bounds
+//     a one-ray-per-load scan on sm_100) and the two tests run as packed FFMA2 with the sphere scalars
+//     broadcast.  Per sphere: 1 LDS.128 + 7 FFMA2 + 2 FSETP + 2 predicated OR.
+// (3) The closest hit is order independent (each sphere contributes its first root > tmin, the
+//     minimum wins, ties go to the lowest slot: same rule as the LBVH leaves), so own-half, other-half
+//     and far candidates can be resolved in any order.
+// Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const Vec3<float> &o, const Vec3<float> &d, float a,
+                                             Hit<float> &hit) {
+    using N = Num<float>;
+    const float4 s = lds_geom<float>(geom_addr + (uint32_t)id * 16u);
+    float h;
+    const float disc = disc_of<float>(s, o, d, a, h);            // GF hittable.h:41-46
+    if (disc < 0.0f) return;                                     // GF hittable.h:47 (also drops filter false positives)
+    const float sq = N::sqrt(disc);
+    float v = N::div(N::sub(h, sq), a);
+    if (!(N::tmin() < v)) {
+        v = N::div(N::add(h, sq), a);
+        if (!(N::tmin() < v)) return;
+    }
+    if (v < hit.t || (v == hit.t && id < hit.id)) { hit.t = v; hit.id = id; }
+}
+
+__device__ __forceinline__ void push_bits(uint32_t m, int base, unsigned short *list, int stride, int &count) {
+    do {
+        const int k = __ffs(m) - 1;
+        m &= m - 1u;
+        if (count < PAIR_CAP) list[count * stride] = static_cast<unsigned short>(base + k);
+        ++count;
+    } while (m);
+}
+
+#ifndef RT_PAIR_UNROLL
+#define RT_PAIR_UNROLL 16           // slots per unrolled body of the paired scan (8, 16 or 32)
+#endif
+constexpr float RT_FILTER_K = 72.0f * 5.9604644775390625e-08f;      // 72 * 2^-24
+
+struct PairRay { float2 dx, dy, dz, ox, oy, oz, nod; float thr_own, thr_nb; };
+
+// one filt[] record against both rays; bit `bit` of s_own / s_nb is set when the slot is a candidate
+__device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, uint32_t bit, uint32_t &s_own, uint32_t &s_nb) {
+    const float2 cx = make_float2(q.x, q.x), cy = make_float2(q.y, q.y), cz = make_float2(q.z, q.z), nk = make_float2(q.w, q.w);
+    float2 h = __ffma2_rn(cz, r.dz, r.nod);
+    float2 t = __ffma2_rn(cz, r.oz, nk);
+    h = __ffma2_rn(cy, r.dy, h);
+    t = __ffma2_rn(cy, r.oy, t);
+    h = __ffma2_rn(cx, r.dx, h);
+    t = __ffma2_rn(cx, r.ox, t);
+    const float2 v = __ffma2_rn(h, h, t);
+    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_own) : "f"(v.x), "f"(r.thr_own), "r"(bit));
+    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_nb) : "f"(v.y), "f"(r.thr_nb), "r"(bit));
+}
+
+__device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int n, const Vec3<float> &o, const Vec3<float> &d,
+                                                         unsigned short *cand, int stride) {
+    using N = Num<float>;
+    constexpr unsigned FULLMASK = 0xffffffffu;
+    const float a = dot3(d, d);                                     // GF hittable.h:42
+    // per-ray filter constants (any rounding here is inside the 72 * 2^-24 budget)
+    const float inv = N::rcp(N::sqrt(a));
+    const float dx = N::mul(d.x, inv), dy = N::mul(d.y, inv), dz = N::mul(d.z, inv);
+    const float nod = -N::fma(o.x, dx, N::fma(o.y, dy, N::mul(o.z, dz)));
+    const float oo = N::fma(o.x, o.x, N::fma(o.y, o.y, N::mul(o.z, o.z)));
+    const float reach = N::add(N::sqrt(oo), g.bound);
+    const float thr = N::fma(-N::mul(RT_FILTER_K, reach), reach, oo);
+    const bool sane = a > 1e-30f && a < 1e30f && oo < 1e24f;       // false for NaN/inf too: such rays take the exact loop
+    PairRay r;
+    r.dx = make_float2(dx, __shfl_xor_sync(FULLMASK, dx, 1));
+    r.dy = make_float2(dy, __shfl_xor_sync(FULLMASK, dy, 1));
+    r.dz = make_float2(dz, __shfl_xor_sync(FULLMASK, dz, 1));
+    const float ox2 = N::add(o.x, o.x), oy2 = N::add(o.y, o.y), oz2 = N::add(o.z, o.z);
+    r.ox = make_float2(ox2, __shfl_xor_sync(FULLMASK, ox2, 1));
+    r.oy = make_float2(oy2, __shfl_xor_sync(FULLMASK, oy2, 1));
+    r.oz = make_float2(oz2, __shfl_xor_sync(FULLMASK, oz2, 1));
+    r.nod = make_float2(nod, __shfl_xor_sync(FULLMASK, nod, 1));
+    r.thr_own = thr;
+    r.thr_nb = __shfl_xor_sync(FULLMASK, thr, 1);
+
+    const int half = threadIdx.x & 1;
+    const int slot0 = half ? g.n_half : 0;                          // slot id of this half's record 0
+    unsigned short *list_own = cand, *list_nb = cand + PAIR_CAP * stride;
+    int cnt_own = 0, cnt_nb = 0;
+    uint32_t addr = g.filt_addr + (uint32_t)(half * g.half_pad) * 16u;
+    int k0 = 0;
+#pragma unroll 1
+    for (; k0 + RT_PAIR_UNROLL <= g.half_pad; k0 += RT_PAIR_UNROLL, addr += RT_PAIR_UNROLL * 16u) {
+        uint32_t s_own = 0, s_nb = 0;
+#pragma unroll
+        for (int k = 0; k < RT_PAIR_UNROLL; ++k) filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, s_own, s_nb);
+        if (s_own | s_nb) {                                          // about 1 % of (ray, slot) pairs
+            if (s_own) push_bits(s_own, slot0 + k0, list_own, stride, cnt_own);
+            if (s_nb) push_bits(s_nb, slot0 + k0, list_nb, stride, cnt_nb);
+        }
+    }
+#if RT_PAIR_UNROLL > 8
+#pragma unroll 1
+    for (; k0 < g.half_pad; k0 += 8, addr += 8u * 16u) {             // half_pad is a multiple of 8
+        uint32_t s_own = 0, s_nb = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, s_own, s_nb);
+        if (s_own | s_nb) {
+            if (s_own) push_bits(s_own, slot0 + k0, list_own, stride, cnt_own);
+            if (s_nb) push_bits(s_nb, slot0 + k0, list_nb, stride, cnt_nb);
+        }
+    }
+#endif
+    __syncwarp();                                                    // the neighbour's list is read below
+    const int cnt_peer = __shfl_xor_sync(FULLMASK, cnt_nb, 1);       // candidates the neighbour found for MY ray
+    Hit<float> hit;
+    hit.t = N::inf();
+    hit.id = -1;
+    if (sane && cnt_own <= PAIR_CAP && cnt_peer <= PAIR_CAP) {
+#pragma unroll 1
+        for (int k = 0; k < cnt_own; ++k) resolve_slot(g.addr, list_own[k * stride], o, d, a, hit);
+        const unsigned short *peer = list_nb + ((threadIdx.x & 1) ? -1 : 1);
+#pragma unroll 1
+        for (int k = 0; k < cnt_peer; ++k) resolve_slot(g.addr, peer[k * stride], o, d, a, hit);
+#pragma unroll 1
+        for (int k = 0; k < g.n_far; ++k) {
+            int id;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(g.far_addr + (uint32_t)k * 4u));
+            resolve_slot(g.addr, id, o, d, a, hit);
+        }
+    } else {
+        // a list overflowed or the ray is degenerate: the reference's loop, slot by slot
+        hit = rescan_in_order<float>(g.addr, n, o, d, a);
+    }
+    __syncwarp();                                                    // lists are rewritten by the next scan
+    return hit;
+}
+
+// hit_world (GF hittable.h:80-98).  All 32 lanes of the warp must call it together.
+template <typename T>
+__device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
+                                              unsigned short *cand, int stride) {
+    if constexpr (sizeof(T) == 4) {
+        if (g.filter_ok) return closest_hit_paired(g, n, o, d, cand, stride);
+    }
+    return closest_hit_exact<T>(g, n, o, d, cand, stride);
 }
 
 }  // namespace rt

@@ -28,7 +28,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int TRACE_BLOCK = 256;
 
 #ifndef RT_TRACE_MIN_BLOCKS
-#define RT_TRACE_MIN_BLOCKS 2
+#define RT_TRACE_MIN_BLOCKS 3
 #endif
 
 template <typename T> struct DevCamera {
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
         sc = view_of<T>(smem, A.scene);
         cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
-        geo = scan_geom(smem_u32(smem), A.scene.n);
+        geo = scan_geom(smem_u32(smem), A.scene);
     } else {
         // large scenes: geometry through the LBVH in global memory (L1/L2), materials by slot
         sc = view_of<T>(A.scene.base, A.scene);
@@ -478,11 +478,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
     if (ACCEL == RT_ACCEL_LINEAR) {
         stage_scene(smem, scene.base, scene.bytes, &bar);
         cand = reinterpret_cast<unsigned short *>(smem + scene.bytes) + threadIdx.x;
-        geo = scan_geom(smem_u32(smem), scene.n);
+        geo = scan_geom(smem_u32(smem), scene);
     }
     unsigned int n_nodes = 0, n_tests = 0;
     const long long npix = (long long)width * height;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x) {
+    // the closest-hit scan is warp-cooperative: every lane of a warp takes every trip, lanes past the end
+    // trace pixel 0 and store nothing
+    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < npix; k0 += (long long)gridDim.x * blockDim.x) {
+        const bool valid = k0 + threadIdx.x < npix;
+        const long long k = valid ? k0 + threadIdx.x : 0;
         const int j = (int)(k / width), i = (int)(k - (long long)j * width);
         const T fi = static_cast<T>(i), fj = static_cast<T>(j);
         Vec3<T> d;
@@ -492,8 +496,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
         Hit<T> hit;
         if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(bvh, cam.center, d, n_nodes, n_tests);
         else hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
-        ids[k] = hit.id;
-        ts[k] = hit.t;
+        if (valid) {
+            ids[k] = hit.id;
+            ts[k] = hit.t;
+        }
     }
 }
 
@@ -570,6 +576,71 @@ template <typename T, typename Cam> DevCamera<T> to_dev(const Cam &c) {
     return d;
 }
 
+// Conservative filter data of the paired scan (rt_device.cuh).
+//   far set   slots whose |centre| + radius is far above the rest (> 8 x the median, at most 16 of them) or not
+//             finite: they would inflate the per-ray error bound of every slot, so they stay out of the filter
+//             and are tested exactly for every ray (the 1000-unit ground sphere of the reference's scenes);
+//   filt[]    (cx, cy, cz, -(|c|^2 - r^2)) for the other slots, the slot list cut into two halves (one per lane
+//             of a pair), each padded to a multiple of 8 with records that never pass (nk = -inf);
+//   bound     max |centre| + radius over the filtered slots, rounded up.
+// The filter is switched off (exact scan) for scenes whose scale would let the bound over- or underflow.
+struct FilterPlan {
+    bool ok = false;
+    int n_half = 0, half_pad = 0;
+    float bound = 0.f;
+    std::vector<float4> filt;
+    std::vector<int> far;
+};
+
+FilterPlan plan_filter(const std::vector<float4> &g) {
+    FilterPlan P;
+    const int n = (int)g.size();
+    if (getenv("RT_NO_FILTER")) return P;                                 // debugging aid: exact scan
+    std::vector<double> ext((size_t)n);
+    std::vector<double> finite_ext;
+    for (int i = 0; i < n; ++i) {
+        const float4 &s = g[(size_t)i];
+        const double e = std::sqrt((double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z) + std::fabs((double)s.w);
+        ext[(size_t)i] = e;
+        if (std::isfinite(e)) finite_ext.push_back(e);
+    }
+    double median = 0.0;
+    if (!finite_ext.empty()) {
+        std::nth_element(finite_ext.begin(), finite_ext.begin() + (long)(finite_ext.size() / 2), finite_ext.end());
+        median = finite_ext[finite_ext.size() / 2];
+    }
+    std::vector<char> is_far((size_t)n, 0);
+    std::vector<std::pair<double, int>> big;
+    for (int i = 0; i < n; ++i) {
+        if (!std::isfinite(ext[(size_t)i])) { is_far[(size_t)i] = 1; P.far.push_back(i); }
+        else if (ext[(size_t)i] > 8.0 * median) big.emplace_back(ext[(size_t)i], i);
+    }
+    std::sort(big.begin(), big.end(), [](const std::pair<double, int> &x, const std::pair<double, int> &y) { return x.first > y.first; });
+    for (size_t k = 0; k < big.size() && P.far.size() < 16; ++k) { is_far[(size_t)big[k].second] = 1; P.far.push_back(big[k].second); }
+    if (P.far.size() > 16) { P.far.clear(); return P; }                   // many non-finite slots: exact scan
+    std::sort(P.far.begin(), P.far.end());
+    double bound = 0.0;
+    for (int i = 0; i < n; ++i) if (!is_far[(size_t)i]) bound = std::max(bound, ext[(size_t)i]);
+    if (!(bound > 1e-12 && bound < 1e12)) {
+        if (bound == 0.0 && (int)P.far.size() == n) bound = 1.0;          // nothing filtered
+        else { P.far.clear(); return P; }
+    }
+    P.bound = (float)(bound * (1.0 + 1e-6));
+    P.n_half = (n + 1) / 2;
+    P.half_pad = (P.n_half + 7) & ~7;
+    const float4 never = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    P.filt.assign((size_t)2 * P.half_pad, never);
+    for (int i = 0; i < n; ++i) {
+        if (is_far[(size_t)i]) continue;
+        const float4 &s = g[(size_t)i];
+        const double k = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z - (double)s.w * s.w;
+        const int half = i >= P.n_half, idx = i - half * P.n_half;
+        P.filt[(size_t)half * P.half_pad + idx] = make_float4(s.x, s.y, s.z, (float)(-k));
+    }
+    P.ok = true;
+    return P;
+}
+
 template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, int n) {
     using V4 = typename Num<T>::vec4;
     if (!ctx || !slots || n <= 0 || n > (1 << 24)) return RT_EINVAL;
@@ -579,7 +650,16 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     const size_t geom_bytes = n8 * sizeof(V4);
     const size_t matl_bytes = (size_t)n * sizeof(V4);
     const size_t rinv_bytes = ((size_t)n * sizeof(T) + 15) & ~(size_t)15;
-    const size_t total = geom_bytes + matl_bytes + type_bytes + rinv_bytes;
+    // float scenes: the conservative filter of the paired scan (rt_device.cuh), built here once per scene
+    FilterPlan plan;
+    if (sizeof(T) == 4) {
+        std::vector<float4> g((size_t)n);
+        for (int i = 0; i < n; ++i) g[(size_t)i] = make_float4((float)slots[i].cx, (float)slots[i].cy, (float)slots[i].cz, (float)slots[i].r);
+        plan = plan_filter(g);
+    }
+    const size_t filt_bytes = plan.filt.size() * sizeof(float4);
+    const size_t far_bytes = (plan.far.size() * sizeof(int) + 15) & ~(size_t)15;
+    const size_t total = geom_bytes + matl_bytes + type_bytes + rinv_bytes + filt_bytes + far_bytes;
     std::vector<unsigned char> host(total, 0);
     V4 *geom = reinterpret_cast<V4 *>(host.data());
     V4 *matl = reinterpret_cast<V4 *>(host.data() + geom_bytes);
@@ -594,6 +674,9 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
         type[i] = s.type;
         rinv[i] = T(1) / static_cast<T>(s.r);                    // IEEE division == the device's rcp.rn
     }
+    if (filt_bytes) std::memcpy(host.data() + geom_bytes + matl_bytes + type_bytes + rinv_bytes, plan.filt.data(), filt_bytes);
+    if (!plan.far.empty())
+        std::memcpy(host.data() + geom_bytes + matl_bytes + type_bytes + rinv_bytes + filt_bytes, plan.far.data(), plan.far.size() * sizeof(int));
     if (ctx->scene_dev) { RT_CUDA(cudaFree(ctx->scene_dev)); ctx->scene_dev = nullptr; }
     RT_CUDA(cudaMalloc(&ctx->scene_dev, total));
     RT_CUDA(cudaMemcpyAsync(ctx->scene_dev, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
@@ -604,6 +687,13 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     ctx->blob.type_off = (uint32_t)(geom_bytes + matl_bytes);
     ctx->blob.rinv_off = (uint32_t)(geom_bytes + matl_bytes + type_bytes);
     ctx->blob.n = n;
+    ctx->blob.filt_off = (uint32_t)(geom_bytes + matl_bytes + type_bytes + rinv_bytes);
+    ctx->blob.far_off = (uint32_t)(geom_bytes + matl_bytes + type_bytes + rinv_bytes + filt_bytes);
+    ctx->blob.filter_ok = plan.ok ? 1 : 0;
+    ctx->blob.n_half = plan.n_half;
+    ctx->blob.half_pad = plan.half_pad;
+    ctx->blob.n_far = (int)plan.far.size();
+    ctx->blob.bound = plan.bound;
     ctx->scene_prec = (int)sizeof(T);
     // a new scene invalidates the LBVH; keep the float geometry for its host-side classification
     for (void *&m : ctx->bvh_mem) if (m) { cudaFree(m); m = nullptr; }
