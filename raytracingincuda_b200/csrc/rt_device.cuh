@@ -397,8 +397,14 @@ __device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const V
                                              Hit<float> &hit) {
     using N = Num<float>;
     const float4 s = lds_geom<float>(geom_addr + (uint32_t)id * 16u);
-    float h;
-    const float disc = disc_of<float>(s, o, d, a, h);            // GF hittable.h:41-46
+    const float ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
+    const float h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
+    const float q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
+    const float c = N::fma(-s.w, s.w, q);
+    // sphere behind the origin (h < 0, origin outside): m = a*c >= 0, so sqrt(disc) <= |h| and both roots are <= 0 < tmin
+    // in the reference's float arithmetic too -- skip the square root and the divisions
+    if (h < 0.0f && c > 0.0f) return;
+    const float disc = N::fma(h, h, -N::mul(a, c));              // GF hittable.h:41-46
     if (disc < 0.0f) return;                                     // GF hittable.h:47 (also drops filter false positives)
     const float sq = N::sqrt(disc);
     float v = N::div(N::sub(h, sq), a);
@@ -498,11 +504,13 @@ __device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int 
     hit.t = N::inf();
     hit.id = -1;
     if (sane && cnt_own <= PAIR_CAP && cnt_peer <= PAIR_CAP) {
-#pragma unroll 1
-        for (int k = 0; k < cnt_own; ++k) resolve_slot(g.addr, list_own[k * stride], o, d, a, hit);
         const unsigned short *peer = list_nb + ((threadIdx.x & 1) ? -1 : 1);
+        const int total = cnt_own + cnt_peer;
 #pragma unroll 1
-        for (int k = 0; k < cnt_peer; ++k) resolve_slot(g.addr, peer[k * stride], o, d, a, hit);
+        for (int k = 0; k < total; ++k) {                            // one loop: trip count max(own + peer) over the warp
+            const int id = k < cnt_own ? list_own[k * stride] : peer[(k - cnt_own) * stride];
+            resolve_slot(g.addr, id, o, d, a, hit);
+        }
 #pragma unroll 1
         for (int k = 0; k < g.n_far; ++k) {
             int id;
