@@ -192,6 +192,14 @@ int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t 
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
 
+/* Diagnostics: audit of the conservative pre-filter the float linear scan runs ahead of the reference's
+ * exact discriminant (GF hittable.h:41-47).  n_rays synthetic rays (camera rays, bounce-like rays and rays
+ * grazing sphere silhouettes within a few ulp) are tested against every filtered slot both ways.
+ * out[0] (ray, slot) pairs, out[1] pairs with reference discriminant >= 0, out[2] pairs the filter passes,
+ * out[3] pairs with discriminant >= 0 that the filter rejected (the guarantee: always 0), out[4] rays skipped
+ * as degenerate.  All zero when the scene uses the exact scan only. */
+int rt_filter_audit(rt_ctx *ctx, const rt_camera *cam, uint64_t seed, uint64_t n_rays, uint64_t out[5]);
+
 /* Single-process multi-GPU helpers (the CLI's --gpus N): a frame buffer on this context's device that
  * other contexts render into with rt_opts.place_rows, after enabling peer (NVLink P2P) access. */
 int rt_frame_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -88,6 +88,7 @@ SYMBOLS = {
     "rt_primary_hits": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "rt_filter_audit": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rt_get_stats": (C.c_int, [_P, _P]),
     "rt_frame_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "rt_frame_free": (C.c_int, [_P, _P]),
@@ -293,6 +294,12 @@ class Renderer:
         fn = lib().rt_primary_hits64 if double else lib().rt_primary_hits
         _ck(fn(self._ctx, C.byref(cam), ids.ctypes.data, t.ctypes.data), "rt_primary_hits")
         return ids, t
+
+    def filter_audit(self, cam, n_rays, seed=1):
+        """rt_filter_audit: dict(pairs, exact_pass, filter_pass, missed, skipped)."""
+        out = (C.c_uint64 * 5)()
+        _ck(lib().rt_filter_audit(self._ctx, C.byref(cam), seed, n_rays, out), "rt_filter_audit")
+        return dict(zip(("pairs", "exact_pass", "filter_pass", "missed", "skipped"), [int(v) for v in out]))
 
     def stats(self):
         s = Stats()

@@ -431,6 +431,33 @@ constexpr float RT_FILTER_K = 72.0f * 5.9604644775390625e-08f;      // 72 * 2^-2
 
 struct PairRay { float2 dx, dy, dz, ox, oy, oz, nod; float thr_own, thr_nb; };
 
+// per-ray constants of the filter (any rounding here is inside the 72 * 2^-24 budget)
+struct FilterRay { float a, dx, dy, dz, ox2, oy2, oz2, nod, thr; bool sane; };
+
+__device__ __forceinline__ FilterRay filter_ray(const Vec3<float> &o, const Vec3<float> &d, float bound) {
+    using N = Num<float>;
+    FilterRay f;
+    f.a = dot3(d, d);                                              // GF hittable.h:42
+    const float inv = N::rcp(N::sqrt(f.a));
+    f.dx = N::mul(d.x, inv); f.dy = N::mul(d.y, inv); f.dz = N::mul(d.z, inv);
+    f.nod = -N::fma(o.x, f.dx, N::fma(o.y, f.dy, N::mul(o.z, f.dz)));
+    const float oo = N::fma(o.x, o.x, N::fma(o.y, o.y, N::mul(o.z, o.z)));
+    const float reach = N::add(N::sqrt(oo), bound);
+    f.thr = N::fma(-N::mul(RT_FILTER_K, reach), reach, oo);
+    f.ox2 = N::add(o.x, o.x); f.oy2 = N::add(o.y, o.y); f.oz2 = N::add(o.z, o.z);
+    f.sane = f.a > 1e-30f && f.a < 1e30f && oo < 1e24f;           // false for NaN/inf too: such rays take the exact loop
+    return f;
+}
+
+// the filter value of one filt[] record, scalar form (each component of the packed FFMA2 chain in
+// filter_pair rounds exactly like these fmaf)
+__device__ __forceinline__ float filter_value(const float4 q, const FilterRay &f) {
+    using N = Num<float>;
+    const float h = N::fma(q.x, f.dx, N::fma(q.y, f.dy, N::fma(q.z, f.dz, f.nod)));
+    const float t = N::fma(q.x, f.ox2, N::fma(q.y, f.oy2, N::fma(q.z, f.oz2, q.w)));
+    return N::fma(h, h, t);
+}
+
 // one filt[] record against both rays; bit `bit` of s_own / s_nb is set when the slot is a candidate
 __device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, uint32_t bit, uint32_t &s_own, uint32_t &s_nb) {
     const float2 cx = make_float2(q.x, q.x), cy = make_float2(q.y, q.y), cz = make_float2(q.z, q.z), nk = make_float2(q.w, q.w);
@@ -449,20 +476,14 @@ __device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int 
                                                          unsigned short *cand, int stride) {
     using N = Num<float>;
     constexpr unsigned FULLMASK = 0xffffffffu;
-    const float a = dot3(d, d);                                     // GF hittable.h:42
-    // per-ray filter constants (any rounding here is inside the 72 * 2^-24 budget)
-    const float inv = N::rcp(N::sqrt(a));
-    const float dx = N::mul(d.x, inv), dy = N::mul(d.y, inv), dz = N::mul(d.z, inv);
-    const float nod = -N::fma(o.x, dx, N::fma(o.y, dy, N::mul(o.z, dz)));
-    const float oo = N::fma(o.x, o.x, N::fma(o.y, o.y, N::mul(o.z, o.z)));
-    const float reach = N::add(N::sqrt(oo), g.bound);
-    const float thr = N::fma(-N::mul(RT_FILTER_K, reach), reach, oo);
-    const bool sane = a > 1e-30f && a < 1e30f && oo < 1e24f;       // false for NaN/inf too: such rays take the exact loop
+    const FilterRay fr = filter_ray(o, d, g.bound);
+    const float a = fr.a, dx = fr.dx, dy = fr.dy, dz = fr.dz, nod = fr.nod, thr = fr.thr;
+    const bool sane = fr.sane;
     PairRay r;
     r.dx = make_float2(dx, __shfl_xor_sync(FULLMASK, dx, 1));
     r.dy = make_float2(dy, __shfl_xor_sync(FULLMASK, dy, 1));
     r.dz = make_float2(dz, __shfl_xor_sync(FULLMASK, dz, 1));
-    const float ox2 = N::add(o.x, o.x), oy2 = N::add(o.y, o.y), oz2 = N::add(o.z, o.z);
+    const float ox2 = fr.ox2, oy2 = fr.oy2, oz2 = fr.oz2;
     r.ox = make_float2(ox2, __shfl_xor_sync(FULLMASK, ox2, 1));
     r.oy = make_float2(oy2, __shfl_xor_sync(FULLMASK, oy2, 1));
     r.oz = make_float2(oz2, __shfl_xor_sync(FULLMASK, oz2, 1));

@@ -503,6 +503,95 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Audit of the paired scan's conservative filter (rt_filter_audit): every generated ray is tested
+// against every filtered slot with BOTH the reference's exact discriminant (disc_of) and the filter
+// (filter_ray / filter_value, the code the scan runs).  out[0] pairs, out[1] exact passes (disc >= 0),
+// out[2] filter passes, out[3] MISSES (exact pass the filter rejected: must be 0), out[4] rays skipped
+// as degenerate.  Ray kinds, by index: 0 jittered camera rays; 1 bounce-like rays (origin on a random
+// sphere, random direction); 2 / 3 rays aimed at the silhouette of a random sphere from the camera /
+// from a point on another sphere, nudged by a few ulp -- the discriminant's sign is decided by rounding.
+__global__ void __launch_bounds__(256) filter_audit_kernel(const __grid_constant__ SceneBlob scene,
+                                                           const __grid_constant__ DevCamera<float> cam, int width, int height,
+                                                           uint32_t seed_lo, uint32_t seed_hi, unsigned long long n_rays,
+                                                           unsigned long long *__restrict__ out) {
+    using N = Num<float>;
+    const SceneView<float> sc = view_of<float>(scene.base, scene);
+    const float4 *filt = reinterpret_cast<const float4 *>(static_cast<const char *>(scene.base) + scene.filt_off);
+    const int *far = reinterpret_cast<const int *>(static_cast<const char *>(scene.base) + scene.far_off);
+    unsigned long long pairs = 0, epass = 0, fpass = 0, missed = 0, skipped = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_rays;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        Philox ph;
+        ph.open(seed_lo, seed_hi, (uint32_t)k, (uint32_t)(k >> 32), 0x7fffffffu);
+        ph.block(0);
+        const float u0 = N::uniform(ph.w[0], 0), u1 = N::uniform(ph.w[1], 0), u2 = N::uniform(ph.w[2], 0), u3 = N::uniform(ph.w[3], 0);
+        ph.block(1);
+        const float u4 = N::uniform(ph.w[0], 0), u5 = N::uniform(ph.w[1], 0), u6 = N::uniform(ph.w[2], 0), u7 = N::uniform(ph.w[3], 0);
+        const int kind = (int)(k & 3ull);
+        Vec3<float> o = cam.center, d;
+        auto on_sphere = [&](int slot, float ua, float ub) {            // point on the surface of `slot`
+            const float4 s = sc.geom[slot];
+            const float z = 1.f - 2.f * ua, rr = sqrtf(fmaxf(0.f, 1.f - z * z)), phi = 6.2831853f * ub;
+            Vec3<float> p;
+            p.x = s.x + s.w * rr * cosf(phi); p.y = s.y + s.w * z; p.z = s.z + s.w * rr * sinf(phi);
+            return p;
+        };
+        const int sa = min(scene.n - 1, (int)(u0 * scene.n)), sb = min(scene.n - 1, (int)(u1 * scene.n));
+        if (kind == 0) {
+            const float px = u0 * width, py = u1 * height;
+            d.x = fmaf(py, cam.dv.x, fmaf(px, cam.du.x, cam.pixel00.x)) - o.x;
+            d.y = fmaf(py, cam.dv.y, fmaf(px, cam.du.y, cam.pixel00.y)) - o.y;
+            d.z = fmaf(py, cam.dv.z, fmaf(px, cam.du.z, cam.pixel00.z)) - o.z;
+        } else if (kind == 1) {
+            o = on_sphere(sa, u2, u3);
+            const float z = 1.f - 2.f * u4, rr = sqrtf(fmaxf(0.f, 1.f - z * z)), phi = 6.2831853f * u5;
+            const float len = 0.01f + 2.f * u6;
+            d.x = len * rr * cosf(phi); d.y = len * z; d.z = len * rr * sinf(phi);
+        } else {
+            if (kind == 3) o = on_sphere(sa, u2, u3);
+            // tangent point of sphere sb seen from o: c + r * (-(r/D) v + sqrt(1 - (r/D)^2) n), v = unit(c - o), n perp v
+            const float4 s = sc.geom[sb];
+            Vec3<float> v; v.x = s.x - o.x; v.y = s.y - o.y; v.z = s.z - o.z;
+            const float D = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+            if (!(D > fabsf(s.w) * 1.0001f) || !(s.w > 0.f)) { ++skipped; continue; }
+            v.x /= D; v.y /= D; v.z /= D;
+            Vec3<float> e; e.x = u4 - .5f; e.y = u5 - .5f; e.z = u6 - .5f;           // random vector, made perpendicular to v
+            const float ev = e.x * v.x + e.y * v.y + e.z * v.z;
+            e.x -= ev * v.x; e.y -= ev * v.y; e.z -= ev * v.z;
+            const float el = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+            if (!(el > 1e-3f)) { ++skipped; continue; }
+            e.x /= el; e.y /= el; e.z /= el;
+            const float q = s.w / D, w = sqrtf(fmaxf(0.f, 1.f - q * q));
+            const float nudge = 1.f + (u7 - .5f) * 4e-6f;                            // a few ulp either side of tangency
+            Vec3<float> p;
+            p.x = s.x + s.w * nudge * (-q * v.x + w * e.x); p.y = s.y + s.w * nudge * (-q * v.y + w * e.y); p.z = s.z + s.w * nudge * (-q * v.z + w * e.z);
+            const float len = 0.05f + 3.f * u3 * u3;
+            d.x = (p.x - o.x) * len; d.y = (p.y - o.y) * len; d.z = (p.z - o.z) * len;
+        }
+        const FilterRay fr = filter_ray(o, d, scene.bound);
+        if (!fr.sane) { ++skipped; continue; }
+        int next_far = 0;
+        for (int i = 0; i < scene.n; ++i) {
+            if (next_far < scene.n_far && far[next_far] == i) { ++next_far; continue; }   // far slots are not filtered
+            const int half = i >= scene.n_half;
+            const float4 q = filt[half * scene.half_pad + (i - half * scene.n_half)];
+            float h;
+            const float disc = disc_of<float>(sc.geom[i], o, d, fr.a, h);
+            const bool e = disc >= 0.0f, f = filter_value(q, fr) >= fr.thr;
+            ++pairs;
+            epass += e; fpass += f; missed += (e && !f);
+        }
+    }
+    unsigned long long v[5] = {pairs, epass, fpass, missed, skipped};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], off);
+        if ((threadIdx.x & 31) == 0 && v[q]) atomicAdd(out + q, v[q]);
+    }
+}
+
 }  // namespace rt
 
 // ==============================================================================================
@@ -1275,6 +1364,26 @@ int rt_enable_peer_access(rt_ctx *ctx, int peer_device) {
     const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RT_OK; }
     return e == cudaSuccess ? RT_OK : (int)e;
+}
+
+int rt_filter_audit(rt_ctx *ctx, const rt_camera *cam, uint64_t seed, uint64_t n_rays, uint64_t out[5]) {
+    if (!ctx || !cam || !out) return RT_EINVAL;
+    if (!ctx->scene_dev) return RT_ENOSCENE;
+    if (ctx->scene_prec != 4) return RT_EPRECISION;
+    for (int q = 0; q < 5; ++q) out[q] = 0;
+    if (!ctx->blob.filter_ok || n_rays == 0) return RT_OK;             // exact scan in use: nothing to audit
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
+    const unsigned long long blocks = (n_rays + 255) / 256;
+    const int grid = (int)std::min<unsigned long long>(blocks, (unsigned long long)ctx->sm_count * 8);
+    filter_audit_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->blob, to_dev<float>(*cam), cam->width, cam->height, (uint32_t)seed,
+                                                       (uint32_t)(seed >> 32), n_rays, ctx->queue);
+    RT_CUDA(cudaGetLastError());
+    unsigned long long h[5];
+    RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 5; ++q) out[q] = h[q];
+    return RT_OK;
 }
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats) {

@@ -233,6 +233,86 @@ def test_slot_counts_around_block_boundaries(renderer, n):
     assert np.array_equal(bits(img), bits(ref))
 
 
+# ---------------------------------------------- conservative pre-filter of the paired scan ------
+def shifted_scene(scale, shift):
+    """Scene 1 scaled and moved away from the coordinate origin: the filter's error bound grows with the
+    distance of centres and ray origins from the origin, so this is where a missed candidate would show."""
+    s = rt.scene(1).copy()
+    s["c"] = (s["c"].astype(np.float64) * scale + np.asarray(shift, dtype=np.float64)).astype(np.float32)
+    s["r"] = (s["r"].astype(np.float64) * scale).astype(np.float32)
+    return s
+
+
+AUDIT_SCENES = {
+    "scene1": lambda: rt.scene(1), "scene2": lambda: rt.scene(2), "scene3": lambda: rt.scene(3),
+    "shifted": lambda: shifted_scene(1.0, (37.0, 3.0, -21.0)),
+    "tiny": lambda: shifted_scene(1e-3, (0.004, 0.0, 0.002)),
+    "huge": lambda: shifted_scene(4096.0, (0.0, 0.0, 0.0)),
+    "concentric": lambda: concentric_scene(),
+}
+
+
+@pytest.mark.parametrize("name", sorted(AUDIT_SCENES))
+def test_filter_never_rejects_a_slot_the_reference_accepts(renderer, name):
+    """rt_filter_audit: about 10^9 (ray, slot) pairs per scene, a quarter of the rays grazing a silhouette
+    within a few ulp.  Not one pair with reference discriminant >= 0 may fail the filter."""
+    slots = AUDIT_SCENES[name]()
+    renderer.upload_scene(slots)
+    a = renderer.filter_audit(rt.camera(320, 192), n_rays=max(1 << 18, (1 << 30) // len(slots)), seed=7)
+    assert a["pairs"] > 0, "the filter is expected to be active for this scene"
+    assert a["missed"] == 0, a
+    assert a["exact_pass"] > 1000 and a["filter_pass"] >= a["exact_pass"]
+    # on the reference's scenes the filter must also stay selective: at most 1.5x the reference's own pass count
+    # (the camera 13 units away from a millimetre-sized copy of the scene is correct but not selective)
+    if name.startswith("scene"):
+        assert a["filter_pass"] <= 1.5 * a["exact_pass"], a
+
+
+@pytest.mark.parametrize("name", ["shifted", "tiny", "huge"])
+def test_shifted_and_scaled_scenes_bit_exact_vs_oracle(renderer, name):
+    slots = AUDIT_SCENES[name]()
+    renderer.upload_scene(slots)
+    cam = rt.camera(96, 64, 4, 10)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(slots, O.camera(96, 64))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+    img = renderer.render(cam)
+    ref, seg = O.render(slots, O.camera(96, 64, 4, 10))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(img), bits(ref))
+
+
+def test_equal_t_ties_go_to_the_lowest_slot(renderer):
+    """Duplicates of one sphere in both halves of the slot list and in the far set: the reference's strict
+    `t < closest` keeps the first (lowest) slot, whatever order the candidates are resolved in."""
+    base = rt.scene(1)
+    n = 64
+    s = base[:n].copy()
+    for dst in (5, 40, 63):                      # half 0, half 1, last slot
+        s[dst] = s[2]
+    s[50] = s[0]                                 # a second copy of the ground sphere (far set)
+    renderer.upload_scene(s)
+    cam = rt.camera(160, 96, 4, 8)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(s, O.camera(160, 96))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+    assert (ids == 2).any() and not np.isin(ids, (5, 40, 63, 50)).any()
+    img = renderer.render(cam)
+    ref, _ = O.render(s, O.camera(160, 96, 4, 8))
+    assert np.array_equal(bits(img), bits(ref))
+
+
+def test_scene_outside_the_filter_range_takes_the_exact_scan(renderer):
+    """Scenes whose scale would over/underflow the filter bound are scanned with the exact discriminant only."""
+    slots = shifted_scene(1e-14, (0.0, 0.0, 0.0))
+    renderer.upload_scene(slots)
+    a = renderer.filter_audit(rt.camera(64, 40), n_rays=1024)
+    assert a["pairs"] == 0
+    ids, t = renderer.primary_hits(rt.camera(64, 40))
+    oids, ot = O.primary(slots, O.camera(64, 40))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+
+
 # ------------------------------------------------------------------ LBVH (RT_ACCEL_LBVH) ------
 @pytest.mark.parametrize("scene_id", [1, 2, 3])
 def test_lbvh_primary_equals_linear_scan(renderer, scene_id):
