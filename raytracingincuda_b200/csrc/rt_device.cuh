@@ -99,8 +99,8 @@ struct Philox {
 //   [vec4 matl[n]]       albedo.xyz, param (fuzz for metal, refraction index for dielectric)
 //   [int  type[n4]]
 //   [T    rinv[n]]       1/radius (host IEEE division, the value rcp.rn gives on the device)
-//   [float4 filt[2*half_pad]]  float scenes: centre.xyz, -(|centre|^2 - radius^2) per slot, two halves
-//   [int  far[n_far]]          float scenes: slots kept out of filt[]
+//   [float4 filt[2*half_pad]]  centre.xyz (rounded to float), -(|centre|^2 - radius^2) per slot, two halves
+//   [int  far[n_far]]          slots kept out of filt[]
 // staged into shared memory by one thread with cp.async.bulk + an mbarrier (TMA bulk copy).
 template <typename T> struct SceneView {
     const typename Num<T>::vec4 *geom;
@@ -220,7 +220,7 @@ struct ScanGeom {
     int blocks;           // n / 32 full blocks
     int tail_groups;      // ceil((n % 32) / 8) groups of 8 after the full blocks
     uint32_t tail_mask;   // valid-slot bits of the tail word (slot k of a word <-> bit 31-k)
-    // paired filter scan (float scenes with blob.filter_ok)
+    // paired filter scan (blob.filter_ok)
     uint32_t filt_addr, far_addr;
     int filter_ok, n_half, half_pad, n_far;
     float bound;
@@ -372,7 +372,7 @@ __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, co
 }
 
 // ------------------------------------------------------------------------------------------
-// Paired filter scan (float scenes).  Same answer as closest_hit_exact, about half the issue slots.
+// Paired filter scan.  Same answer as closest_hit_exact, about half the issue slots.
 //
 // (1) Conservative filter.  With d' = d/|d| the reference's discriminant has the sign of
 //         F = (c.d' - o.d')^2 + 2 c.o - (|c|^2 - r^2) - |o|^2          ( = r^2 - dist(centre, ray)^2 )
@@ -393,21 +393,21 @@ __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, co
 //     minimum wins, ties go to the lowest slot: same rule as the LBVH leaves), so own-half, other-half
 //     and far candidates can be resolved in any order.
 // Must be called by all 32 lanes of the warp.
-__device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const Vec3<float> &o, const Vec3<float> &d, float a,
-                                             Hit<float> &hit) {
-    using N = Num<float>;
-    const float4 s = lds_geom<float>(geom_addr + (uint32_t)id * 16u);
-    const float ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
-    const float h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
-    const float q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
-    const float c = N::fma(-s.w, s.w, q);
+template <typename T>
+__device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const Vec3<T> &o, const Vec3<T> &d, T a, Hit<T> &hit) {
+    using N = Num<T>;
+    const typename N::vec4 s = lds_geom<T>(geom_addr + (uint32_t)id * (uint32_t)sizeof(typename N::vec4));
+    const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
+    const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
+    const T q = N::fma(ocz, ocz, N::fma(ocx, ocx, N::mul(ocy, ocy)));
+    const T c = N::fma(-s.w, s.w, q);
     // sphere behind the origin (h < 0, origin outside): m = a*c >= 0, so sqrt(disc) <= |h| and both roots are <= 0 < tmin
-    // in the reference's float arithmetic too -- skip the square root and the divisions
-    if (h < 0.0f && c > 0.0f) return;
-    const float disc = N::fma(h, h, -N::mul(a, c));              // GF hittable.h:41-46
-    if (disc < 0.0f) return;                                     // GF hittable.h:47 (also drops filter false positives)
-    const float sq = N::sqrt(disc);
-    float v = N::div(N::sub(h, sq), a);
+    // in the reference's own arithmetic too -- skip the square root and the divisions
+    if (h < T(0) && c > T(0)) return;
+    const T disc = N::fma(h, h, -N::mul(a, c));                  // GF hittable.h:41-46
+    if (disc < T(0)) return;                                     // GF hittable.h:47 (also drops filter false positives)
+    const T sq = N::sqrt(disc);
+    T v = N::div(N::sub(h, sq), a);
     if (!(N::tmin() < v)) {
         v = N::div(N::add(h, sq), a);
         if (!(N::tmin() < v)) return;
@@ -472,12 +472,21 @@ __device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, ui
     asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_nb) : "f"(v.y), "f"(r.thr_nb), "r"(bit));
 }
 
-__device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int n, const Vec3<float> &o, const Vec3<float> &d,
-                                                         unsigned short *cand, int stride) {
-    using N = Num<float>;
+//
+// Double scenes run the SAME float filter on float-rounded copies of the ray and of the geometry: rounding the
+// inputs moves r^2 - dist^2 by less than the reference's float discriminant error the budget already holds
+// (DESIGN.md section 6), and the candidates are resolved in double.
+template <typename T>
+__device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
+                                                     unsigned short *cand, int stride) {
+    using N = Num<T>;
     constexpr unsigned FULLMASK = 0xffffffffu;
-    const FilterRay fr = filter_ray(o, d, g.bound);
-    const float a = fr.a, dx = fr.dx, dy = fr.dy, dz = fr.dz, nod = fr.nod, thr = fr.thr;
+    Vec3<float> of, df;
+    of.x = (float)o.x; of.y = (float)o.y; of.z = (float)o.z;
+    df.x = (float)d.x; df.y = (float)d.y; df.z = (float)d.z;
+    const FilterRay fr = filter_ray(of, df, g.bound);
+    const T a = sizeof(T) == 4 ? (T)fr.a : dot3(d, d);             // GF hittable.h:42
+    const float dx = fr.dx, dy = fr.dy, dz = fr.dz, nod = fr.nod, thr = fr.thr;
     const bool sane = fr.sane;
     PairRay r;
     r.dx = make_float2(dx, __shfl_xor_sync(FULLMASK, dx, 1));
@@ -521,7 +530,7 @@ __device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int 
 #endif
     __syncwarp();                                                    // the neighbour's list is read below
     const int cnt_peer = __shfl_xor_sync(FULLMASK, cnt_nb, 1);       // candidates the neighbour found for MY ray
-    Hit<float> hit;
+    Hit<T> hit;
     hit.t = N::inf();
     hit.id = -1;
     if (sane && cnt_own <= PAIR_CAP && cnt_peer <= PAIR_CAP) {
@@ -530,17 +539,17 @@ __device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int 
 #pragma unroll 1
         for (int k = 0; k < total; ++k) {                            // one loop: trip count max(own + peer) over the warp
             const int id = k < cnt_own ? list_own[k * stride] : peer[(k - cnt_own) * stride];
-            resolve_slot(g.addr, id, o, d, a, hit);
+            resolve_slot<T>(g.addr, id, o, d, a, hit);
         }
 #pragma unroll 1
         for (int k = 0; k < g.n_far; ++k) {
             int id;
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(g.far_addr + (uint32_t)k * 4u));
-            resolve_slot(g.addr, id, o, d, a, hit);
+            resolve_slot<T>(g.addr, id, o, d, a, hit);
         }
     } else {
         // a list overflowed or the ray is degenerate: the reference's loop, slot by slot
-        hit = rescan_in_order<float>(g.addr, n, o, d, a);
+        hit = rescan_in_order<T>(g.addr, n, o, d, a);
     }
     __syncwarp();                                                    // lists are rewritten by the next scan
     return hit;
@@ -550,9 +559,7 @@ __device__ __forceinline__ Hit<float> closest_hit_paired(const ScanGeom &g, int 
 template <typename T>
 __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
                                               unsigned short *cand, int stride) {
-    if constexpr (sizeof(T) == 4) {
-        if (g.filter_ok) return closest_hit_paired(g, n, o, d, cand, stride);
-    }
+    if (g.filter_ok) return closest_hit_paired<T>(g, n, o, d, cand, stride);
     return closest_hit_exact<T>(g, n, o, d, cand, stride);
 }
 

@@ -741,7 +741,7 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     const size_t rinv_bytes = ((size_t)n * sizeof(T) + 15) & ~(size_t)15;
     // float scenes: the conservative filter of the paired scan (rt_device.cuh), built here once per scene
     FilterPlan plan;
-    if (sizeof(T) == 4) {
+    {
         std::vector<float4> g((size_t)n);
         for (int i = 0; i < n; ++i) g[(size_t)i] = make_float4((float)slots[i].cx, (float)slots[i].cy, (float)slots[i].cz, (float)slots[i].r);
         plan = plan_filter(g);
