@@ -71,22 +71,32 @@ __device__ __forceinline__ T dot3(const Vec3<T> &u, const Vec3<T> &v) {
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (pixel, sample, dimension, block), key = seed.
+// The ten round keys depend on the seed only: the host expands them once (philox_keys) and the
+// kernels read them from the parameter constant bank, so a block is 20 IMAD.WIDE + 20 LOP3.
+struct PhiloxKeys { uint32_t k[20]; };      // k[2r], k[2r+1] = key of round r
+
+inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t ka = (uint32_t)seed, kb = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k[2 * r] = ka; K.k[2 * r + 1] = kb; ka += 0x9E3779B9u; kb += 0xBB67AE85u; }
+    return K;
+}
+
 struct Philox {
-    uint32_t c0, c1, c2, k0, k1;      // c3 (block) is supplied per call
+    uint32_t c0, c1, c2;              // c3 (block) is supplied per call
+    const uint32_t *rk;               // round keys (constant bank)
     uint32_t w[4];
-    __device__ __forceinline__ void open(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel,
-                                         uint32_t sample, uint32_t dim) {
-        c0 = pixel; c1 = sample; c2 = dim; k0 = seed_lo; k1 = seed_hi;
+    __device__ __forceinline__ void open(const PhiloxKeys &keys, uint32_t pixel, uint32_t sample, uint32_t dim) {
+        c0 = pixel; c1 = sample; c2 = dim; rk = keys.k;
     }
     __device__ __forceinline__ void block(uint32_t blk) {
-        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = blk, ka = k0, kb = k1;
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = blk;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
             const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
             const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-            const uint32_t y0 = hi1 ^ x1 ^ ka, y2 = hi0 ^ x3 ^ kb;
+            const uint32_t y0 = hi1 ^ x1 ^ rk[2 * r], y2 = hi0 ^ x3 ^ rk[2 * r + 1];
             x0 = y0; x1 = lo1; x2 = y2; x3 = lo0;
-            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
         }
         w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
     }
@@ -210,8 +220,8 @@ __device__ __forceinline__ uint32_t sign_word(double x) { return (uint32_t)__dou
 // `cand` points at this thread's column of a [CAND_CAP][blockDim.x] uint16 array.
 // After the full blocks a tail of up to three groups of 8 covers n % 32; the geometry array is
 // padded with zero records to a multiple of 8 and `tail_mask` clears the padding's bits.
-constexpr int CAND_CAP = 32;       // exact scan: one list of 32; paired filter scan: two lists of 16 (own ray, neighbour's ray)
-constexpr int PAIR_CAP = CAND_CAP / 2;
+constexpr int CAND_CAP = 32;       // exact scan: a list of 32 uint16 slots per thread; the paired filter scan uses the same
+                                   // 64 bytes per thread as 16 candidate-mask words (PAIR_CHUNK)
 
 template <typename T> struct Hit { T t; int id; };
 
@@ -415,18 +425,11 @@ __device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const V
     if (v < hit.t || (v == hit.t && id < hit.id)) { hit.t = v; hit.id = id; }
 }
 
-__device__ __forceinline__ void push_bits(uint32_t m, int base, unsigned short *list, int stride, int &count) {
-    do {
-        const int k = __ffs(m) - 1;
-        m &= m - 1u;
-        if (count < PAIR_CAP) list[count * stride] = static_cast<unsigned short>(base + k);
-        ++count;
-    } while (m);
-}
-
 #ifndef RT_PAIR_UNROLL
-#define RT_PAIR_UNROLL 16           // slots per unrolled body of the paired scan (8, 16 or 32)
+#define RT_PAIR_UNROLL 16           // records per unrolled body (= per candidate-mask word) of the paired scan: 8 or 16
 #endif
+static_assert(RT_PAIR_UNROLL == 8 || RT_PAIR_UNROLL == 16, "a block's two candidate masks share one 32-bit word");
+constexpr int PAIR_CHUNK = 16;       // blocks per chunk: one 16-bit flag word per ray, [PAIR_CHUNK][blockDim] mask words
 constexpr float RT_FILTER_K = 72.0f * 5.9604644775390625e-08f;      // 72 * 2^-24
 
 struct PairRay { float2 dx, dy, dz, ox, oy, oz, nod; float thr_own, thr_nb; };
@@ -459,7 +462,8 @@ __device__ __forceinline__ float filter_value(const float4 q, const FilterRay &f
 }
 
 // one filt[] record against both rays; bit `bit` of s_own / s_nb is set when the slot is a candidate
-__device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, uint32_t bit, uint32_t &s_own, uint32_t &s_nb) {
+__device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, uint32_t bit_own, uint32_t bit_nb, uint32_t &s_own,
+                                            uint32_t &s_nb) {
     const float2 cx = make_float2(q.x, q.x), cy = make_float2(q.y, q.y), cz = make_float2(q.z, q.z), nk = make_float2(q.w, q.w);
     float2 h = __ffma2_rn(cz, r.dz, r.nod);
     float2 t = __ffma2_rn(cz, r.oz, nk);
@@ -468,8 +472,8 @@ __device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, ui
     h = __ffma2_rn(cx, r.dx, h);
     t = __ffma2_rn(cx, r.ox, t);
     const float2 v = __ffma2_rn(h, h, t);
-    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_own) : "f"(v.x), "f"(r.thr_own), "r"(bit));
-    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_nb) : "f"(v.y), "f"(r.thr_nb), "r"(bit));
+    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_own) : "f"(v.x), "f"(r.thr_own), "r"(bit_own));
+    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; @p or.b32 %0, %0, %3; }" : "+r"(s_nb) : "f"(v.y), "f"(r.thr_nb), "r"(bit_nb));
 }
 
 //
@@ -500,47 +504,74 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
     r.thr_own = thr;
     r.thr_nb = __shfl_xor_sync(FULLMASK, thr, 1);
 
+    // Candidate bookkeeping without a branch in the scan: after every block of 16 (or 8) records the two 16-bit
+    // candidate masks go to this lane's word column in shared memory with one store, and one bit per ray says
+    // whether the block had any candidate.  Blocks are handled in chunks of PAIR_CHUNK (one flag word per ray); the
+    // reference's scenes are a single chunk.
     const int half = threadIdx.x & 1;
-    const int slot0 = half ? g.n_half : 0;                          // slot id of this half's record 0
-    unsigned short *list_own = cand, *list_nb = cand + PAIR_CAP * stride;
-    int cnt_own = 0, cnt_nb = 0;
-    uint32_t addr = g.filt_addr + (uint32_t)(half * g.half_pad) * 16u;
-    int k0 = 0;
-#pragma unroll 1
-    for (; k0 + RT_PAIR_UNROLL <= g.half_pad; k0 += RT_PAIR_UNROLL, addr += RT_PAIR_UNROLL * 16u) {
-        uint32_t s_own = 0, s_nb = 0;
-#pragma unroll
-        for (int k = 0; k < RT_PAIR_UNROLL; ++k) filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, s_own, s_nb);
-        if (s_own | s_nb) {                                          // about 1 % of (ray, slot) pairs
-            if (s_own) push_bits(s_own, slot0 + k0, list_own, stride, cnt_own);
-            if (s_nb) push_bits(s_nb, slot0 + k0, list_nb, stride, cnt_nb);
-        }
-    }
-#if RT_PAIR_UNROLL > 8
-#pragma unroll 1
-    for (; k0 < g.half_pad; k0 += 8, addr += 8u * 16u) {             // half_pad is a multiple of 8
-        uint32_t s_own = 0, s_nb = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, s_own, s_nb);
-        if (s_own | s_nb) {
-            if (s_own) push_bits(s_own, slot0 + k0, list_own, stride, cnt_own);
-            if (s_nb) push_bits(s_nb, slot0 + k0, list_nb, stride, cnt_nb);
-        }
-    }
-#endif
-    __syncwarp();                                                    // the neighbour's list is read below
-    const int cnt_peer = __shfl_xor_sync(FULLMASK, cnt_nb, 1);       // candidates the neighbour found for MY ray
+    uint32_t *words = reinterpret_cast<uint32_t *>(cand - threadIdx.x) + threadIdx.x;   // [PAIR_CHUNK][stride] uint32, my column
+    const uint32_t *peer_words = words + (half ? -1 : 1);
+    const int wstride = stride;                                      // cand points at column threadIdx.x of uint32 words
     Hit<T> hit;
     hit.t = N::inf();
     hit.id = -1;
-    if (sane && cnt_own <= PAIR_CAP && cnt_peer <= PAIR_CAP) {
-        const unsigned short *peer = list_nb + ((threadIdx.x & 1) ? -1 : 1);
-        const int total = cnt_own + cnt_peer;
+    const int slot_own0 = half ? g.n_half : 0, slot_peer0 = half ? 0 : g.n_half;   // slot of record 0: my half / the peer's half
+    uint32_t addr = g.filt_addr + (uint32_t)(half * g.half_pad) * 16u;
+    int k0 = 0;                                                      // record index within the half
+    while (k0 < g.half_pad) {
+        const int chunk0 = k0;
+        uint32_t flags_own = 0, flags_nb = 0;
+        int blk = 0;
 #pragma unroll 1
-        for (int k = 0; k < total; ++k) {                            // one loop: trip count max(own + peer) over the warp
-            const int id = k < cnt_own ? list_own[k * stride] : peer[(k - cnt_own) * stride];
-            resolve_slot<T>(g.addr, id, o, d, a, hit);
+        for (; blk < PAIR_CHUNK && k0 + RT_PAIR_UNROLL <= g.half_pad; ++blk, k0 += RT_PAIR_UNROLL, addr += RT_PAIR_UNROLL * 16u) {
+            uint32_t s_own = 0, s_nb = 0;
+#pragma unroll
+            for (int k = 0; k < RT_PAIR_UNROLL; ++k)
+                filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, 0x10000u << k, s_own, s_nb);
+            words[blk * wstride] = s_own | s_nb;
+            flags_own |= (s_own ? 1u : 0u) << blk;
+            flags_nb |= (s_nb ? 1u : 0u) << blk;
         }
+#if RT_PAIR_UNROLL > 8
+        // the last block of a half may hold a single group of 8 records (half_pad is a multiple of 8)
+        if (blk < PAIR_CHUNK && k0 < g.half_pad && g.half_pad - k0 < RT_PAIR_UNROLL) {
+            uint32_t s_own = 0, s_nb = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, 0x10000u << k, s_own, s_nb);
+            words[blk * wstride] = s_own | s_nb;
+            flags_own |= (s_own ? 1u : 0u) << blk;
+            flags_nb |= (s_nb ? 1u : 0u) << blk;
+            k0 = g.half_pad;
+        }
+#endif
+        __syncwarp();                                                // the neighbour's words are read below
+        uint32_t fo = flags_own, fp = __shfl_xor_sync(FULLMASK, flags_nb, 1);   // fp: blocks of the peer's half with candidates for MY ray
+        if (sane) {
+            uint32_t w = 0;
+            int base = 0;
+#pragma unroll 1
+            while (w | fo | fp) {
+                if (!w) {                                            // next block that holds a candidate for my ray
+                    if (fo) {
+                        const int b = __ffs(fo) - 1;
+                        fo &= fo - 1u;
+                        w = words[b * wstride] & 0xffffu;
+                        base = slot_own0 + chunk0 + b * RT_PAIR_UNROLL;
+                    } else {
+                        const int b = __ffs(fp) - 1;
+                        fp &= fp - 1u;
+                        w = peer_words[b * wstride] >> 16;
+                        base = slot_peer0 + chunk0 + b * RT_PAIR_UNROLL;
+                    }
+                }
+                const int k = __ffs(w) - 1;
+                w &= w - 1u;
+                resolve_slot<T>(g.addr, base + k, o, d, a, hit);
+            }
+        }
+        __syncwarp();                                                // words are rewritten by the next chunk / scan
+    }
+    if (sane) {
 #pragma unroll 1
         for (int k = 0; k < g.n_far; ++k) {
             int id;
@@ -548,10 +579,9 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
             resolve_slot<T>(g.addr, id, o, d, a, hit);
         }
     } else {
-        // a list overflowed or the ray is degenerate: the reference's loop, slot by slot
+        // degenerate ray (NaN/inf/denormal scale): the reference's loop, slot by slot
         hit = rescan_in_order<T>(g.addr, n, o, d, a);
     }
-    __syncwarp();                                                    // lists are rewritten by the next scan
     return hit;
 }
 

@@ -40,7 +40,7 @@ template <typename T> struct DevCamera {
 template <typename T> struct TraceArgs {
     DevCamera<T> cam;
     SceneBlob scene;
-    uint32_t seed_lo, seed_hi;
+    PhiloxKeys keys;                   // Philox round keys of the seed
     int spp, max_depth;
     int width;
     int tile_rows, rank, world;        // local row -> global row (world == 1: identity)
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         // ---- one Philox block per lane and turn, shared by the two consumers: dimension 0 feeds
         //      the camera ray of a fresh sample, dimension depth+1 the scatter of the pending hit ----
         Philox ph;
-        ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, fresh ? 0u : (uint32_t)(depth + 1));
+        ph.open(A.keys, pixel, (uint32_t)sample, fresh ? 0u : (uint32_t)(depth + 1));
         ph.block(0);
         if (ready() && !fresh) {
             // shade the hit found by the previous scan
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             if (!alive || ++depth >= A.max_depth) {                       // GF camera.h:117 / :84,127 -> black
                 end_path(T(0), T(0), T(0));
                 if (state == ACTIVE) {                                    // rare: regenerate right away
-                    ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, 0u);
+                    ph.open(A.keys, pixel, (uint32_t)sample, 0u);
                     ph.block(0);
                 }
             }
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
 // from a point on another sphere, nudged by a few ulp -- the discriminant's sign is decided by rounding.
 __global__ void __launch_bounds__(256) filter_audit_kernel(const __grid_constant__ SceneBlob scene,
                                                            const __grid_constant__ DevCamera<float> cam, int width, int height,
-                                                           uint32_t seed_lo, uint32_t seed_hi, unsigned long long n_rays,
+                                                           const __grid_constant__ PhiloxKeys keys, unsigned long long n_rays,
                                                            unsigned long long *__restrict__ out) {
     using N = Num<float>;
     const SceneView<float> sc = view_of<float>(scene.base, scene);
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) filter_audit_kernel(const __grid_constant
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_rays;
          k += (unsigned long long)gridDim.x * blockDim.x) {
         Philox ph;
-        ph.open(seed_lo, seed_hi, (uint32_t)k, (uint32_t)(k >> 32), 0x7fffffffu);
+        ph.open(keys, (uint32_t)k, (uint32_t)(k >> 32), 0x7fffffffu);
         ph.block(0);
         const float u0 = N::uniform(ph.w[0], 0), u1 = N::uniform(ph.w[1], 0), u2 = N::uniform(ph.w[2], 0), u3 = N::uniform(ph.w[3], 0);
         ph.block(1);
@@ -945,7 +945,7 @@ template <typename Cam> struct WavefrontImpl<float, Cam> {
         A.bvh_min_active = 0;
         A.cam = to_dev<float>(cam);
         A.scene = ctx->blob;
-        A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
+        A.keys = philox_keys(o.seed);
         A.spp = cam.spp; A.max_depth = cam.max_depth;
         A.width = cam.width;
         A.tile_rows = o.tile_rows; A.rank = o.rank;
@@ -1042,7 +1042,7 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     if (const char *e = getenv("RT_BVH_MIN_ACTIVE")) A.bvh_min_active = atoi(e);
     A.cam = to_dev<T>(cam);
     A.scene = ctx->blob;
-    A.seed_lo = (uint32_t)o.seed; A.seed_hi = (uint32_t)(o.seed >> 32);
+    A.keys = philox_keys(o.seed);
     A.spp = cam.spp; A.max_depth = cam.max_depth;
     A.width = cam.width;
     A.tile_rows = o.tile_rows; A.rank = o.rank;
@@ -1376,8 +1376,8 @@ int rt_filter_audit(rt_ctx *ctx, const rt_camera *cam, uint64_t seed, uint64_t n
     RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
     const unsigned long long blocks = (n_rays + 255) / 256;
     const int grid = (int)std::min<unsigned long long>(blocks, (unsigned long long)ctx->sm_count * 8);
-    filter_audit_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->blob, to_dev<float>(*cam), cam->width, cam->height, (uint32_t)seed,
-                                                       (uint32_t)(seed >> 32), n_rays, ctx->queue);
+    filter_audit_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->blob, to_dev<float>(*cam), cam->width, cam->height, philox_keys(seed), n_rays,
+                                                       ctx->queue);
     RT_CUDA(cudaGetLastError());
     unsigned long long h[5];
     RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));

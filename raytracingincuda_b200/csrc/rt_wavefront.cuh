@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ TraceArg
         hit.t = P.hit_t[s];
         hit.id = P.hit_id[s];
         Philox ph;
-        ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
+        ph.open(A.keys, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
         ph.block(0);
         const bool alive = scatter(sc, hit, ph, ps);
         if (!alive || ++depth >= A.max_depth) {
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ TraceArg
     }
     if (s >= 0 && state == WF_FRESH) {
         Philox ph;
-        ph.open(A.seed_lo, A.seed_hi, pixel, (uint32_t)sample, 0u);
+        ph.open(A.keys, pixel, (uint32_t)sample, 0u);
         ph.block(0);
         camera_ray(A, (int)(pixel % (uint32_t)A.width), (int)(pixel / (uint32_t)A.width), ph, ps);
         depth = 0;

@@ -302,6 +302,21 @@ def test_equal_t_ties_go_to_the_lowest_slot(renderer):
     assert np.array_equal(bits(img), bits(ref))
 
 
+def test_multi_chunk_scene_bit_exact_vs_oracle(renderer):
+    """1 448 slots: each half of the slot list spans several chunks of candidate-mask words."""
+    slots = rt.scene_scaled(19)
+    assert len(slots) > 1024
+    renderer.upload_scene(slots)
+    cam = rt.camera(120, 72, 3, 8)
+    ids, t = renderer.primary_hits(cam)
+    oids, ot = O.primary(O.scene_scaled(19), O.camera(120, 72))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+    img = renderer.render(cam)
+    ref, seg = O.render(O.scene_scaled(19), O.camera(120, 72, 3, 8))
+    assert renderer.stats().segments == seg
+    assert np.array_equal(bits(img), bits(ref))
+
+
 def test_scene_outside_the_filter_range_takes_the_exact_scan(renderer):
     """Scenes whose scale would over/underflow the filter bound are scanned with the exact discriminant only."""
     slots = shifted_scene(1e-14, (0.0, 0.0, 0.0))

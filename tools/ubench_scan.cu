@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256, 4) scan_kernel(const float4 *scene, float
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     float ox = 13.f + 1e-3f * (tid & 1023), oy = 2.f + 1e-3f * (tid & 511), oz = 3.f - 1e-3f * (tid & 127);
     float dx = -0.9f + 1e-4f * (tid & 255), dy = -0.1f - 1e-4f * (tid & 63), dz = -0.3f + 1e-4f * (tid >> 8);
-    if ((MODE >= 1 && MODE <= 3) || (MODE >= 6 && MODE <= 8)) { const float il = rsqrtf(dx * dx + dy * dy + dz * dz); dx *= il; dy *= il; dz *= il; }
+    if ((MODE >= 1 && MODE <= 3) || (MODE >= 6 && MODE <= 9)) { const float il = rsqrtf(dx * dx + dy * dy + dz * dz); dx *= il; dy *= il; dz *= il; }
     unsigned found = 0;
     float accum = 0.f;
     for (int rep = 0; rep < REPS; ++rep) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, 4) scan_kernel(const float4 *scene, float
                 }
                 if (MODE == 2) { if (~signs) found += __popc(~signs); }
             }
-        } else if (MODE == 6 || MODE == 7 || MODE == 8) {
+        } else if (MODE == 6 || MODE == 7 || MODE == 8 || MODE == 9) {
             // two rays per lane, one sphere per LDS.128: 7 FFMA2 per sphere with the sphere scalars broadcast
             const float ex = ox + 0.37f, ey = oy + 0.11f, ez = oz - 0.23f;                 // second ray
             const float fx = dz, fy = dy, fz = dx;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256, 4) scan_kernel(const float4 *scene, float
                     float2 t = __ffma2_rn(cz, oz2, nk);
                     t = __ffma2_rn(cy, oy2, t);
                     t = __ffma2_rn(cx, ox2, t);
+                    if (MODE == 9) { h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f); }
                     const float2 v = __ffma2_rn(h, h, t);
                     if (MODE == 6 || MODE == 8) {
                         const float2 w = __fadd2_rn(v, nthr2);
@@ -245,6 +246,7 @@ int main() {
     run<6>("r2s16", scene_f, out, cnt, sms, mhz, NS);
     run<7>("r2p16", scene_f, out, cnt, sms, mhz, NS);
     run<8>("r2s32", scene_f, out, cnt, sms, mhz, NS);
+    run<9>("r2p16c", scene_f, out, cnt, sms, mhz, NS);
     run<4>("ffma", scene, out, cnt, sms, mhz, NS * 8.0);
     run<5>("ffma2", scene, out, cnt, sms, mhz, NS * 8.0);
     return 0;
