@@ -25,7 +25,7 @@ for r in rows[2:]:
     tot += n
     insts.append((n, t, src))
 print("total warp-instructions", tot)
-FMA = {"FFMA", "FMUL", "FADD", "IMAD", "HFMA2", "FFMA32I", "FMUL32I", "FADD32I"}
+FMA = {"FFMA", "FFMA2", "FMUL", "FMUL2", "FADD", "FADD2", "IMAD", "HFMA2", "FFMA32I", "FMUL32I", "FADD32I"}
 print("fma-pipe share %.3f" % (sum(v for k, v in by_op.items() if k in FMA) / tot))
 for op, n in by_op.most_common(40):
     print(f"{op:10s} {n:14d} {100*n/tot:6.2f}%  avg-threads {thr[op]/max(1,n):5.1f}")
