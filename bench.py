@@ -199,21 +199,37 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------ reference kernel on the GPU
 def reference_gpu_kernel():
-    """The reference's global-float kernel rebuilt for sm_100 (oracle/_ref), BASELINE config 2,
-    its own render_ms stdout field."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "global-float-cuda-raytrace")
-    if not os.path.exists(exe):
-        return None
+    """The reference's kernels rebuilt for sm_100 (oracle/_ref), BASELINE config 2, their own render_ms stdout field:
+    the global-float variant (the parity target) and, as timing comparators only, the constant- and texture-memory
+    variants the shared-memory scene replaces (scene 1 only, ConstFloat main.cu:73-76)."""
     scene, W, H, spp, depth = WORKLOADS["cfg2"]
-    runs = []
-    with tempfile.TemporaryDirectory() as tmp:
-        for _ in range(2):
-            out = subprocess.check_output([exe, "--scene_id", str(scene), "--width", str(W), "--height", str(H),
-                                           "--samples", str(spp), "--bounces", str(depth), "--threads", "8"], cwd=tmp)
-            runs.append(float(out.decode().split(",")[0]))
-    ms = min(runs)
-    return {"kernel": "GlobalFloat render rebuilt -O3 sm_100, --threads 8", "workload": f"scene {scene}, {W}x{H}, {spp} spp, {depth} bounces",
-            "render_ms": round(ms, 3), "value": round(W * H * spp / ms / 1e3, 3), "unit": METRIC}
+
+    def run(exe_name):
+        exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
+        if not os.path.exists(exe):
+            return None
+        runs = []
+        with tempfile.TemporaryDirectory() as tmp:
+            for _ in range(2):
+                out = subprocess.check_output([exe, "--scene_id", str(scene), "--width", str(W), "--height", str(H),
+                                               "--samples", str(spp), "--bounces", str(depth), "--threads", "8"], cwd=tmp)
+                runs.append(float(out.decode().split(",")[0]))
+        ms = min(runs)
+        return {"render_ms": round(ms, 3), "value": round(W * H * spp / ms / 1e3, 3)}
+
+    g = run("global-float-cuda-raytrace")
+    if g is None:
+        return None
+    line = {"kernel": "GlobalFloat render rebuilt -O3 sm_100, --threads 8", "workload": f"scene {scene}, {W}x{H}, {spp} spp, {depth} bounces",
+            "render_ms": g["render_ms"], "value": g["value"], "unit": METRIC}
+    for key, exe_name in (("const_float", "const-float-cuda-raytrace"), ("tex_float", "tex-float-cuda-raytrace")):
+        try:
+            v = run(exe_name)
+        except Exception as e:                                    # a comparator that fails must not take the bench line with it
+            v = {"error": str(e)[:120]}
+        if v is not None:
+            line[key] = v
+    return line
 
 
 # ------------------------------------------------------------------ B200 arm ----------------

@@ -122,6 +122,15 @@ int rt_scene_generate64(int scene_id, rt_slot64 *out, int capacity);      /* GD 
  * grid [-half, half)^2; half = 158 gives 99 860 slots. */
 int rt_scene_generate_scaled(int half, rt_slot *out, int capacity);
 
+/* General scene loader (lifts the scene-1-only limit of the reference's const/tex variants,
+ * ConstFloat main.cu:73-76, TexFloat main.cu:68-72).  Text file, one slot per line, '#' starts a comment:
+ *     cx cy cz radius type albedo_r albedo_g albedo_b fuzz ri        (type: 0 lambertian, 1 metal, 2 dielectric)
+ * rt_scene_write_text prints every float with %.9g, which round-trips float32, so write -> read is lossless.
+ * rt_scene_read_text returns the slot count (writes at most `capacity` slots when `out` is non-NULL) or a
+ * negative RT_E* code (RT_EIO: cannot open; RT_EINVAL: malformed line). */
+int rt_scene_read_text(const char *path, rt_slot *out, int capacity);
+int rt_scene_write_text(const char *path, const rt_slot *slots, int n);
+
 /* camera::initialize() (GF camera.h:33-68) for the fixed view of GF main.cu:100-124. */
 int rt_camera_init(rt_camera *cam, int width, int height, int spp, int max_depth);
 int rt_camera_init64(rt_camera64 *cam, int width, int height, int spp, int max_depth);

@@ -89,6 +89,8 @@ SYMBOLS = {
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "rt_filter_audit": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
+    "rt_scene_read_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
+    "rt_scene_write_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
     "rt_get_stats": (C.c_int, [_P, _P]),
     "rt_frame_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "rt_frame_free": (C.c_int, [_P, _P]),
@@ -139,6 +141,21 @@ def scene_scaled(half):
     out = np.zeros(n, dtype=SLOT_DTYPE)
     L.rt_scene_generate_scaled(half, out.ctypes.data, n)
     return out
+
+
+def load_scene(path):
+    """rt_scene_read_text: slots of a text scene file (one sphere per line)."""
+    n = lib().rt_scene_read_text(os.fsencode(path), None, 0)
+    if n < 0:
+        raise RtError(n, "rt_scene_read_text")
+    slots = np.zeros(n, dtype=SLOT_DTYPE)
+    lib().rt_scene_read_text(os.fsencode(path), slots.ctypes.data, n)
+    return slots
+
+
+def save_scene(path, slots):
+    slots = np.ascontiguousarray(slots, dtype=SLOT_DTYPE)
+    _ck(lib().rt_scene_write_text(os.fsencode(path), slots.ctypes.data, len(slots)), "rt_scene_write_text")
 
 
 def camera(width, height, spp=10, max_depth=25, double=False):

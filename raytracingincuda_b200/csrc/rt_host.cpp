@@ -260,6 +260,43 @@ int rt_scene_generate_scaled(int half, rt_slot *out, int capacity) {
     return generate<float>(-half, half, -half, half, out, capacity);
 }
 
+// General scene loader: one slot per line, "cx cy cz radius type ar ag ab fuzz ri", '#' comments.
+int rt_scene_read_text(const char *path, rt_slot *out, int capacity) {
+    if (!path) return RT_EINVAL;
+    FILE *f = std::fopen(path, "r");
+    if (!f) return RT_EIO;
+    char line[512];
+    int n = 0, rc = RT_OK;
+    while (std::fgets(line, sizeof line, f)) {
+        if (char *hash = std::strchr(line, '#')) *hash = '\0';
+        rt_slot s;
+        std::memset(&s, 0, sizeof s);
+        int type = 0;
+        const int got = std::sscanf(line, "%f %f %f %f %d %f %f %f %f %f", &s.cx, &s.cy, &s.cz, &s.r, &type, &s.albedo[0], &s.albedo[1],
+                                    &s.albedo[2], &s.fuzz, &s.ri);
+        if (got <= 0) continue;                                   // blank or comment-only line
+        if (got != 10 || type < RT_LAMBERTIAN || type > RT_DIELECTRIC) { rc = RT_EINVAL; break; }
+        s.type = type;
+        if (out && n < capacity) out[n] = s;
+        ++n;
+    }
+    std::fclose(f);
+    return rc == RT_OK ? n : rc;
+}
+
+int rt_scene_write_text(const char *path, const rt_slot *slots, int n) {
+    if (!path || !slots || n < 0) return RT_EINVAL;
+    FILE *f = std::fopen(path, "w");
+    if (!f) return RT_EIO;
+    std::fprintf(f, "# cx cy cz radius type(0 lambertian, 1 metal, 2 dielectric) albedo_r albedo_g albedo_b fuzz ri\n");
+    for (int i = 0; i < n; ++i) {
+        const rt_slot &s = slots[i];
+        std::fprintf(f, "%.9g %.9g %.9g %.9g %d %.9g %.9g %.9g %.9g %.9g\n", s.cx, s.cy, s.cz, s.r, s.type, s.albedo[0], s.albedo[1],
+                     s.albedo[2], s.fuzz, s.ri);
+    }
+    return std::fclose(f) == 0 ? RT_OK : RT_EIO;
+}
+
 int rt_camera_init(rt_camera *cam, int width, int height, int spp, int max_depth) {
     return camera_setup<float>(cam, width, height, spp, max_depth);
 }

@@ -4,7 +4,7 @@
 // Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
 // setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
 // (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
-// (--seed, --precision, --gpus, --gather, --accel, --kernel, --scaled_half, --prefix, --no-ppm, --stats) defaults to the reference's
+// (--seed, --precision, --gpus, --gather, --accel, --kernel, --scaled_half, --scene_file, --dump_scene, --prefix, --no-ppm, --stats) defaults to the reference's
 // behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
 // (global_float_benchmark.sh:53-74) stays valid.
 #include "rt_b200.h"
@@ -54,6 +54,7 @@ struct Args {
     int accel = RT_ACCEL_LINEAR;
     int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix, gather = "p2p";
+    std::string scene_file, dump_scene;     // general scene loader (float): read the slots from / write them to a text file
 };
 
 int to_int(const std::string &name, const std::string &text) {
@@ -80,7 +81,7 @@ Args parse(int argc, char **argv) {
         if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
         const bool flag_only = (name == "no-ppm" || name == "stats");
         static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
-                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel", "gather"};
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel", "gather", "scene_file", "dump_scene"};
         bool ok = false;
         for (const char *n : known) ok = ok || name == n;
         if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
@@ -100,6 +101,8 @@ Args parse(int argc, char **argv) {
         else if (name == "split") a.split = value;
         else if (name == "prefix") a.prefix = value;
         else if (name == "gather") a.gather = value;
+        else if (name == "scene_file") a.scene_file = value;
+        else if (name == "dump_scene") a.dump_scene = value;
         else if (name == "accel") { a.lbvh = (value == "lbvh"); a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : RT_ACCEL_LINEAR); }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
         else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
@@ -164,11 +167,15 @@ int main(int argc, char **argv) {
         frame64.resize(npix * 3);
     } else {
         // --scaled_half H: the scaled scene of BASELINE config 5 (grid [-H,H)^2) instead of scene_id
-        n = a.scaled_half > 0 ? rt_scene_generate_scaled(a.scaled_half, nullptr, 0) : rt_scene_generate(a.scene_id, nullptr, 0);
-        if (n <= 0) { std::cerr << "Error: bad --scaled_half" << "\n"; return 1; }
+        // --scene_file F: any list of spheres (rt_scene_read_text) -- the const/tex variants of the reference only take scene 1
+        if (!a.scene_file.empty()) n = rt_scene_read_text(a.scene_file.c_str(), nullptr, 0);
+        else n = a.scaled_half > 0 ? rt_scene_generate_scaled(a.scaled_half, nullptr, 0) : rt_scene_generate(a.scene_id, nullptr, 0);
+        if (n <= 0) { std::cerr << "Error: bad --scaled_half or --scene_file (" << rt_error_string(n) << ")" << "\n"; return 1; }
         slots.resize(static_cast<size_t>(n));
-        if (a.scaled_half > 0) rt_scene_generate_scaled(a.scaled_half, slots.data(), n);
+        if (!a.scene_file.empty()) rt_scene_read_text(a.scene_file.c_str(), slots.data(), n);
+        else if (a.scaled_half > 0) rt_scene_generate_scaled(a.scaled_half, slots.data(), n);
         else rt_scene_generate(a.scene_id, slots.data(), n);
+        if (!a.dump_scene.empty()) CHECK(rt_scene_write_text(a.dump_scene.c_str(), slots.data(), n));
         for (auto &d : dev) CHECK(rt_upload_scene(d.ctx, slots.data(), n));
         frame.resize(npix * 3);
     }

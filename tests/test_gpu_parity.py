@@ -503,6 +503,34 @@ def test_cli_end_to_end(tmp_path):
     assert np.array_equal(got, (256 * x).astype(int).reshape(-1))
 
 
+def test_cli_scene_file_round_trip(tmp_path):
+    """General scene loader: --dump_scene writes the generated slots, --scene_file renders them back to the same PPM;
+    a hand-written three-sphere file renders to the oracle's image."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "raytracingincuda_b200", "bin", "b200-raytrace")
+    common = ["--width", "64", "--height", "40", "--samples", "4", "--bounces", "6"]
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    p = subprocess.run([exe, "--scene_id", "3", *common, "--dump_scene", str(tmp_path / "s3.txt")], cwd=a, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    p = subprocess.run([exe, "--scene_id", "3", *common, "--scene_file", str(tmp_path / "s3.txt")], cwd=b, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    name = "b200_float_scene3_64x40_4samples_6bounces_8threadsPerBlockRow.ppm"
+    assert (a / name).read_bytes() == (b / name).read_bytes()
+    (tmp_path / "mini.txt").write_text("# ground, a glass ball, a metal ball\n0 -1000 0 1000 0 0.5 0.5 0.5 0 0\n"
+                                        "0 1 0 1 2 0 0 0 0 1.5\n4 1 0 1 1 0.7 0.6 0.5 0 0\n")
+    c = tmp_path / "c"
+    c.mkdir()
+    p = subprocess.run([exe, "--scene_id", "9", *common, "--scene_file", str(tmp_path / "mini.txt")], cwd=c, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    slots = rt.load_scene(tmp_path / "mini.txt")
+    assert len(slots) == 3 and list(slots["type"]) == [0, 2, 1]
+    ref, _ = O.render(slots, O.camera(64, 40, 4, 6))
+    rt.ppm_write(str(tmp_path / "want.ppm"), ref)
+    assert (c / "b200_float_scene9_64x40_4samples_6bounces_8threadsPerBlockRow.ppm").read_bytes() == (tmp_path / "want.ppm").read_bytes()
+
+
 @pytest.mark.parametrize("w,h", [(96, 70), (50, 33)])
 def test_place_rows_writes_the_full_frame_in_place(renderer, w, h):
     """rt_opts.place_rows: each rank stores its rows at their global positions of one device frame

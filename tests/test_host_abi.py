@@ -171,3 +171,31 @@ def test_ppm_compare_tool(tmp_path):
     r = run([exe, "a.ppm", "c.ppm"], tmp_path)
     assert r.returncode == 3 and not json.loads(r.stdout)["within_tolerance"]
     assert run([exe, "a.ppm", "missing.ppm"], tmp_path).returncode == 1
+
+
+def test_scene_text_round_trip(tmp_path):
+    """rt_scene_write_text / rt_scene_read_text (general scene loader): %.9g round-trips float32, so all three
+    reference scenes come back byte for byte; comments and blank lines are skipped."""
+    for sid in (1, 2, 3):
+        slots = rt.scene(sid)
+        path = tmp_path / f"scene{sid}.txt"
+        rt.save_scene(path, slots)
+        with open(path, "a") as f:
+            f.write("\n   # trailing comment\n")
+        back = rt.load_scene(path)
+        assert back.tobytes() == slots.tobytes()
+
+
+def test_scene_text_errors(tmp_path):
+    with pytest.raises(rt.RtError) as e:
+        rt.load_scene(tmp_path / "missing.txt")
+    assert e.value.code == -4                                   # RT_EIO
+    bad = tmp_path / "bad.txt"
+    bad.write_text("0 0 0 1 0 0.5 0.5 0.5 0 0\n1 2 3\n")
+    with pytest.raises(rt.RtError) as e:
+        rt.load_scene(bad)
+    assert e.value.code == -1                                   # RT_EINVAL: short line
+    bad.write_text("0 0 0 1 7 0.5 0.5 0.5 0 0\n")
+    with pytest.raises(rt.RtError) as e:
+        rt.load_scene(bad)
+    assert e.value.code == -1                                   # RT_EINVAL: unknown material type
