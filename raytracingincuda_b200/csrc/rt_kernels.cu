@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     unsigned int n_nodes = 0, n_tests = 0;
     constexpr bool LB = (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4);
     BvhTrav tv;                                   // LBVH only: resumable traversal (stack in local memory)
+    BvhStack bvh_stack;
     tv.node = -1;
 
     const int lane = threadIdx.x & 31;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
                 // and the node loop never runs with a nearly empty warp
                 const int flying_lanes = __popc(__ballot_sync(FULL, tv.node >= 0));
                 if (flying_lanes == 0 || (flying_lanes < A.bvh_min_active && step > 0)) break;
-                if (tv.node >= 0) bvh_step(A.bvh, ps.o, ps.d, tv, n_nodes, n_tests);
+                if (tv.node >= 0) bvh_step(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
             }
             landed = flying && tv.node < 0;
             if (landed) hit = tv.hit;

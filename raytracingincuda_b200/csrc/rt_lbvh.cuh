@@ -153,42 +153,41 @@ __device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const 
 
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));      // 1 MUFU; 2 ulp, covered by the 1.001 factor below
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // 1 MUFU; 2 ulp, covered by the 1.001 factor below
     return y;
 }
 
 // entry parameter of the inflated box, or +inf when the ray cannot touch it before `limit`.
-// The slabs are (bound - o) * inv -- subtract first: fma(bound, inv, -o*inv) would cancel badly for
-// origins far from the coordinate origin and break the conservative guarantee.
+// The slabs are ((bound - o) -/+ delta) * inv -- subtract the origin first: fma(bound, inv, -o*inv) would cancel badly
+// for origins far from the coordinate origin and break the conservative guarantee.
 __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, float hx, float hy, float hz, float rmin,
                                                const Vec3<float> &o, const Vec3<float> &inv, float limit) {
-    const float fx = fmaxf(fabsf(lx - o.x), fabsf(hx - o.x));
-    const float fy = fmaxf(fabsf(ly - o.y), fabsf(hy - o.y));
-    const float fz = fmaxf(fabsf(lz - o.z), fabsf(hz - o.z));
+    const float ax = lx - o.x, bx = hx - o.x, ay = ly - o.y, by = hy - o.y, az = lz - o.z, bz = hz - o.z;
+    const float fx = fmaxf(fabsf(ax), fabsf(bx)), fy = fmaxf(fabsf(ay), fabsf(by)), fz = fmaxf(fabsf(az), fabsf(bz));
     const float D2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
     const float delta = fmaf(sqrt_approx(fmaf(BVH_KEPS, D2, rmin * rmin)) - rmin, 1.001f, 1e-7f);
-    const float t0x = (lx - delta - o.x) * inv.x, t1x = (hx + delta - o.x) * inv.x;
-    const float t0y = (ly - delta - o.y) * inv.y, t1y = (hy + delta - o.y) * inv.y;
-    const float t0z = (lz - delta - o.z) * inv.z, t1z = (hz + delta - o.z) * inv.z;
+    const float t0x = (ax - delta) * inv.x, t1x = (bx + delta) * inv.x;
+    const float t0y = (ay - delta) * inv.y, t1y = (by + delta) * inv.y;
+    const float t0z = (az - delta) * inv.z, t1z = (bz + delta) * inv.z;
     const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
     const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    const bool ok = tn <= fmaf(fabsf(tf), 1e-4f, tf) + 1e-30f && tf >= 0.0f && tn <= limit;
+    const bool ok = tn <= fminf(fmaf(fabsf(tf), 1e-4f, tf) + 1e-30f, limit) && tf >= 0.0f;
     return ok ? tn : __int_as_float(0x7f800000);
 }
 
-// Resumable traversal state of one ray.  The stack lives in local memory (L1 resident) and
-// survives across the turns of the persistent loop, so a warp can interleave "a few traversal
-// steps for everybody" with shading/regeneration of the lanes that finished: the lanes of a warp
-// need very different numbers of node visits (mean 18, tail > 100 for rays grazing the ground),
-// and waiting for the slowest lane left 6 of 32 lanes active in the node loop.
+// Resumable traversal state of one ray.  The scalars live in registers; the stack (node id and entry
+// parameter packed into one 64-bit word) lives in local memory (L1 resident) and survives across the
+// turns of the persistent loop, so a warp can interleave "a few traversal steps for everybody" with
+// shading/regeneration of the lanes that finished: the lanes of a warp need very different numbers of
+// node visits (mean 18, tail > 100 for rays grazing the ground), and waiting for the slowest lane left
+// 6 of 32 lanes active in the node loop.
+struct BvhStack { unsigned long long e[BVH_STACK]; };
 struct BvhTrav {
     int node;             // current internal node, -1 = no traversal in flight
     int sp;
     float a;
     Vec3<float> inv;      // 1/d
     Hit<float> hit;
-    int stack[BVH_STACK];
-    float tstack[BVH_STACK];
 };
 
 __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv,
@@ -212,7 +211,7 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
 }
 
 // one node visit; sets tv.node = -1 when the traversal is complete
-__device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv,
+__device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv, BvhStack &st,
                                          unsigned &n_nodes, unsigned &n_tests) {
     const float inf = Num<float>::inf();
     ++n_nodes;
@@ -235,8 +234,7 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     }
     if (tl < inf && tr < inf) {
         const bool left_first = tl <= tr;
-        tv.stack[tv.sp] = left_first ? right : left;
-        tv.tstack[tv.sp] = left_first ? tr : tl;
+        st.e[tv.sp] = ((unsigned long long)__float_as_uint(left_first ? tr : tl) << 32) | (unsigned int)(left_first ? right : left);
         ++tv.sp;
         tv.node = left_first ? left : right;
         return;
@@ -245,9 +243,11 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     if (tr < inf) { tv.node = right; return; }
     // pop, skipping subtrees the current best hit already rules out
     tv.node = -1;
+    const float keep = tv.hit.t * 1.0001f + 1e-6f;
     while (tv.sp > 0) {
         --tv.sp;
-        if (tv.tstack[tv.sp] <= tv.hit.t * 1.0001f + 1e-6f) { tv.node = tv.stack[tv.sp]; break; }
+        const unsigned long long e = st.e[tv.sp];
+        if (__uint_as_float((unsigned int)(e >> 32)) <= keep) { tv.node = (int)(unsigned int)e; break; }
     }
 }
 
@@ -255,8 +255,9 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
 __device__ __forceinline__ Hit<float> bvh_closest_hit(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d,
                                                       unsigned &n_nodes, unsigned &n_tests) {
     BvhTrav tv;
+    BvhStack st;
     bvh_start(bv, o, d, tv, n_tests);
-    while (tv.node >= 0) bvh_step(bv, o, d, tv, n_nodes, n_tests);
+    while (tv.node >= 0) bvh_step(bv, o, d, tv, st, n_nodes, n_tests);
     return tv.hit;
 }
 
