@@ -25,7 +25,10 @@
 namespace rt {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int TRACE_BLOCK = 256;
+#ifndef RT_TRACE_BLOCK
+#define RT_TRACE_BLOCK 256
+#endif
+constexpr int TRACE_BLOCK = RT_TRACE_BLOCK;     // threads per CTA of the path tracer (a multiple of 32)
 
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 3
