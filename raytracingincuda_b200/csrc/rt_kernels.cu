@@ -1041,7 +1041,7 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     A.bvh_steps = 8;
     for (int m = ctx->bvh.m; m > 0; m >>= 1) A.bvh_steps += 1;
     if (A.bvh_steps > 32) A.bvh_steps = 32;
-    A.bvh_min_active = 0;
+    A.bvh_min_active = 6;              // measured: +2.4 % on scene 1, +1.4 % on the 99 860-slot scene against 0
     if (const char *e = getenv("RT_BVH_STEPS")) A.bvh_steps = atoi(e) > 0 ? atoi(e) : A.bvh_steps;   // tuning knobs
     if (const char *e = getenv("RT_BVH_MIN_ACTIVE")) A.bvh_min_active = atoi(e);
     A.cam = to_dev<T>(cam);
