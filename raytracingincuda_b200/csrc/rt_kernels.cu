@@ -25,6 +25,7 @@
 namespace rt {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int ACCEL_LBVH_COMPACT = 3;      // internal: RT_ACCEL_LBVH with one box inflation per ray (compact scenes, rt_lbvh.cuh)
 #ifndef RT_TRACE_BLOCK
 #define RT_TRACE_BLOCK 256
 #endif
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         sc = view_of<T>(A.scene.base, A.scene);
     }
     unsigned int n_nodes = 0, n_tests = 0;
-    constexpr bool LB = (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4);
+    constexpr bool LB = ((ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT) && sizeof(T) == 4);
+    constexpr bool RAYD = (ACCEL == ACCEL_LBVH_COMPACT);
     BvhTrav tv;                                   // LBVH only: resumable traversal (stack in local memory)
     BvhStack bvh_stack;
     tv.node = -1;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             // ---- LBVH: start the traversal of the new ray, then a bounded number of node visits for
             //      every lane with a traversal in flight ----
             const bool launched = ready();
-            if (launched) bvh_start(A.bvh, ps.o, ps.d, tv, n_tests);
+            if (launched) bvh_start<RAYD>(A.bvh, ps.o, ps.d, tv, n_tests);
             const bool flying = launched || (state == ACTIVE && !idle);
 #pragma unroll 1
             for (int step = 0; step < A.bvh_steps; ++step) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
                 // and the node loop never runs with a nearly empty warp
                 const int flying_lanes = __popc(__ballot_sync(FULL, tv.node >= 0));
                 if (flying_lanes == 0 || (flying_lanes < A.bvh_min_active && step > 0)) break;
-                if (tv.node >= 0) bvh_step(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
+                if (tv.node >= 0) bvh_step<RAYD>(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
             }
             landed = flying && tv.node < 0;
             if (landed) hit = tv.hit;
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         atomicAdd(A.queue + 1, seg);
         atomicAdd(A.queue + 2, pth);
     }
-    if (ACCEL == RT_ACCEL_LBVH) {
+    if (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT) {
         unsigned long long nod = n_nodes, tst = n_tests;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -816,8 +818,17 @@ int build_lbvh(rt_ctx *ctx) {
     }
     const float diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) +
                                  (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    // spheres far larger than the scene (the ground) and far smaller than the rest (the reference's never-written slot is a
+    // zero-radius sphere; it would force the smallest-radius inflation of every box above it) stay out of the tree
+    std::vector<float> radii((size_t)n);
+    for (int i = 0; i < n; ++i) radii[(size_t)i] = std::fabs(g[(size_t)i].w);
+    std::nth_element(radii.begin(), radii.begin() + n / 2, radii.end());
+    const float r_med = radii[(size_t)(n / 2)];
     std::vector<int> small_idx, big_idx;
-    for (int i = 0; i < n; ++i) (g[(size_t)i].w > 0.25f * diag ? big_idx : small_idx).push_back(i);
+    for (int i = 0; i < n; ++i) {
+        const float r = std::fabs(g[(size_t)i].w);
+        ((r > 0.25f * diag || r < 0.05f * r_med) ? big_idx : small_idx).push_back(i);
+    }
     if (big_idx.size() > 64) { small_idx.resize((size_t)n); for (int i = 0; i < n; ++i) small_idx[(size_t)i] = i; big_idx.clear(); }
     const int m = (int)small_idx.size(), nbig = (int)big_idx.size();
     for (int q = 0; q < 3; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
@@ -908,6 +919,24 @@ int build_lbvh(rt_ctx *ctx) {
     ctx->bvh.nodes = nodes; ctx->bvh.geom = geom_sorted; ctx->bvh.slot = slot_sorted;
     ctx->bvh.big_geom = big_geom; ctx->bvh.big_slot = big_slot;
     ctx->bvh.m = m; ctx->bvh.nbig = nbig;
+    // bounds and smallest radius of the tree's spheres.  The scene counts as compact when the single per-ray box inflation
+    // (bvh_start<true>) stays below 5 % of the smallest radius for every origin within one bounds-diagonal of the tree.
+    float rmin_all = INFINITY, diag2 = 0.f;
+    for (int q = 0; q < 3; ++q) { ctx->bvh.blo[q] = INFINITY; ctx->bvh.bhi[q] = -INFINITY; }
+    for (int i : small_idx) {
+        const float4 &sph = g[(size_t)i];
+        const float c[3] = {sph.x, sph.y, sph.z}, rr = std::fabs(sph.w);
+        for (int q = 0; q < 3; ++q) { ctx->bvh.blo[q] = std::min(ctx->bvh.blo[q], c[q] - rr); ctx->bvh.bhi[q] = std::max(ctx->bvh.bhi[q], c[q] + rr); }
+        rmin_all = std::min(rmin_all, rr);
+    }
+    for (int q = 0; q < 3; ++q) diag2 += (ctx->bvh.bhi[q] - ctx->bvh.blo[q]) * (ctx->bvh.bhi[q] - ctx->bvh.blo[q]);
+    ctx->bvh.rmin_all = (m > 0 && std::isfinite(rmin_all)) ? rmin_all : 0.f;
+    ctx->bvh.compact = 0;
+    if (m > 1 && ctx->bvh.rmin_all > 0.f && std::isfinite(diag2)) {
+        const float reach = 2.f * std::sqrt(diag2);
+        const float delta = std::sqrt(BVH_KEPS * reach * reach + rmin_all * rmin_all) - rmin_all;
+        ctx->bvh.compact = (delta <= 0.05f * rmin_all && !getenv("RT_BVH_NO_COMPACT")) ? 1 : 0;
+    }
     ctx->bvh_ready = true;
     return RT_OK;
 }
@@ -1032,7 +1061,9 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     int grid = 0;
     int rc = lbvh ? build_lbvh(ctx) : RT_OK;
     if (rc) return rc;
-    rc = lbvh ? launch_shape<T, RT_ACCEL_LBVH>(ctx, smem, &grid) : launch_shape<T, RT_ACCEL_LINEAR>(ctx, smem, &grid);
+    const bool compact = lbvh && ctx->bvh.compact;
+    rc = compact ? launch_shape<T, ACCEL_LBVH_COMPACT>(ctx, smem, &grid)
+                 : (lbvh ? launch_shape<T, RT_ACCEL_LBVH>(ctx, smem, &grid) : launch_shape<T, RT_ACCEL_LINEAR>(ctx, smem, &grid));
     if (rc) return rc;
     TraceArgs<T> A;
     A.bvh = ctx->bvh;
@@ -1063,7 +1094,8 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
     if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
     ctx->stats.grid = grid;
-    if (lbvh) trace_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    if (compact) trace_kernel<T, ACCEL_LBVH_COMPACT><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    else if (lbvh) trace_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     else trace_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     RT_CUDA(cudaGetLastError());
     ctx->stats.launches += 1;

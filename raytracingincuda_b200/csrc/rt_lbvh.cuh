@@ -33,6 +33,10 @@ struct BvhView {
     const float4 *big_geom;   // [nbig] spheres kept out of the tree
     const int *big_slot;
     int m, nbig;
+    // bounds of the tree's spheres (centre -/+ radius), its smallest radius, and whether the scene is compact enough for the
+    // traversal with ONE inflation per ray (bvh_start<true>) instead of one square root per box
+    float blo[3], bhi[3], rmin_all;
+    int compact;
 };
 
 constexpr float BVH_KEPS = 16.0f * 5.9604645e-8f;   // 16 * 2^-24
@@ -175,6 +179,18 @@ __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, flo
     return ok ? tn : __int_as_float(0x7f800000);
 }
 
+// Same test with an inflation fixed per ray (op = o + delta, om = o - delta): 6 subtractions, 6 products, no square root.
+__device__ __forceinline__ float bvh_box_entry_ray(float lx, float ly, float lz, float hx, float hy, float hz, const Vec3<float> &op,
+                                                   const Vec3<float> &om, const Vec3<float> &inv, float limit) {
+    const float t0x = (lx - op.x) * inv.x, t1x = (hx - om.x) * inv.x;
+    const float t0y = (ly - op.y) * inv.y, t1y = (hy - om.y) * inv.y;
+    const float t0z = (lz - op.z) * inv.z, t1z = (hz - om.z) * inv.z;
+    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    const bool ok = tn <= fminf(fmaf(fabsf(tf), 1e-4f, tf) + 1e-30f, limit) && tf >= 0.0f;
+    return ok ? tn : __int_as_float(0x7f800000);
+}
+
 // Resumable traversal state of one ray.  The scalars live in registers; the stack (node id and entry
 // parameter packed into one 64-bit word) lives in local memory (L1 resident) and survives across the
 // turns of the persistent loop, so a warp can interleave "a few traversal steps for everybody" with
@@ -188,8 +204,10 @@ struct BvhTrav {
     float a;
     Vec3<float> inv;      // 1/d
     Hit<float> hit;
+    Vec3<float> op, om;   // compact scenes (bvh_start<true>): o + delta, o - delta with one inflation for every box
 };
 
+template <bool RAYD = false>
 __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv,
                                           unsigned &n_tests) {
     using N = Num<float>;
@@ -208,9 +226,26 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
     }
     tv.inv.x = 1.0f / d.x; tv.inv.y = 1.0f / d.y; tv.inv.z = 1.0f / d.z;
     tv.node = 0;
+    if (RAYD) {
+        // One inflation for the whole traversal: the per-box formula evaluated at the farthest corner of the TREE's bounds
+        // and at the tree's smallest radius bounds every box's own inflation from above (it grows with the distance and
+        // shrinks with the radius), so the traversal stays conservative for any origin; it is only tight -- and chosen by
+        // the host -- when the scene is compact.  The extra 8 ulp of |o| + |box| cover the rounding of o +/- delta and of
+        // the subtractions against it.
+        const float fx = fmaxf(fabsf(bv.blo[0] - o.x), fabsf(bv.bhi[0] - o.x));
+        const float fy = fmaxf(fabsf(bv.blo[1] - o.y), fabsf(bv.bhi[1] - o.y));
+        const float fz = fmaxf(fabsf(bv.blo[2] - o.z), fabsf(bv.bhi[2] - o.z));
+        const float D2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+        const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+        const float delta = fmaf(sqrt_approx(fmaf(BVH_KEPS, D2, bv.rmin_all * bv.rmin_all)) - bv.rmin_all, 1.001f, 1e-7f) +
+                            4.8e-7f * (omax + fmaxf(fmaxf(fx, fy), fz));
+        tv.op.x = o.x + delta; tv.op.y = o.y + delta; tv.op.z = o.z + delta;
+        tv.om.x = o.x - delta; tv.om.y = o.y - delta; tv.om.z = o.z - delta;
+    }
 }
 
 // one node visit; sets tv.node = -1 when the traversal is complete
+template <bool RAYD = false>
 __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o, const Vec3<float> &d, BvhTrav &tv, BvhStack &st,
                                          unsigned &n_nodes, unsigned &n_tests) {
     const float inf = Num<float>::inf();
@@ -220,8 +255,14 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     const float4 q2 = __ldg(bv.nodes + 4 * (size_t)node + 2), q3 = __ldg(bv.nodes + 4 * (size_t)node + 3);
     const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
     const float limit = tv.hit.t * 1.0001f + 1e-6f;
-    float tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, tv.inv, limit);
-    float tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, tv.inv, limit);
+    float tl, tr;
+    if (RAYD) {
+        tl = bvh_box_entry_ray(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tv.op, tv.om, tv.inv, limit);
+        tr = bvh_box_entry_ray(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tv.op, tv.om, tv.inv, limit);
+    } else {
+        tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, tv.inv, limit);
+        tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, tv.inv, limit);
+    }
     if (tl < inf && left < 0) {
         bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, tv.a, tv.hit);
         ++n_tests;
