@@ -81,6 +81,7 @@ typedef struct rt_camera64 {
 enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
 enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2 };   /* AUTO: LBVH for float scenes with >= 256 slots */
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
+enum { RT_PBINS_AUTO = 0, RT_PBINS_OFF = 1, RT_PBINS_ON = 2 };   /* AUTO: on wherever it applies */
 
 /* Per-call options.  Zero-initialise, then set what you need (rt_opts_default does that). */
 typedef struct rt_opts {
@@ -95,7 +96,9 @@ typedef struct rt_opts {
     int32_t place_rows;   /* RT_SPLIT_ROWS only: out_rgb is the FULL frame (width*height*3, device memory -- may be a
                            * peer GPU's, see rt_enable_peer_access) and this rank's rows are stored at their global
                            * positions: the row gather becomes direct stores over NVLink, no separate copy */
-    int32_t reserved[6];
+    int32_t primary_bins; /* RT_PBINS_*: camera rays resolved against per-tile candidate lists built on the device
+                           * before the frame (megakernel + linear scan; same image bit for bit).  0 = on */
+    int32_t reserved[5];
 } rt_opts;
 
 typedef struct rt_stats {

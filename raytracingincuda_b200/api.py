@@ -49,7 +49,7 @@ class Camera64(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("split", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("tile_rows", C.c_int32), ("accel", C.c_int32), ("threads", C.c_int32), ("kernel", C.c_int32),
-                ("place_rows", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("place_rows", C.c_int32), ("primary_bins", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -204,14 +204,15 @@ def ppm_quantise(rgb):
 
 ACCEL_LINEAR, ACCEL_LBVH, ACCEL_AUTO = 0, 1, 2
 KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
+PBINS_AUTO, PBINS_OFF, PBINS_ON = 0, 1, 2
 
 
 def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_LINEAR,
-              kernel=KERNEL_MEGA):
+              kernel=KERNEL_MEGA, primary_bins=PBINS_AUTO):
     o = Opts()
     lib().rt_opts_default(C.byref(o))
     o.seed, o.split, o.rank, o.world, o.tile_rows, o.threads = seed, split, rank, world, tile_rows, threads
-    o.accel, o.kernel = accel, kernel
+    o.accel, o.kernel, o.primary_bins = accel, kernel, primary_bins
     return o
 
 

@@ -58,6 +58,9 @@ template <typename T> struct TraceArgs {
     BvhView bvh;                       // RT_ACCEL_LBVH only
     int bvh_steps;                     // at most this many node visits per loop turn ...
     int bvh_min_active;                // ... and the round ends once fewer lanes than this are still traversing
+    const unsigned short *bins;        // trace_kernel_pb only: per-tile candidate lists of the camera rays (rt_primary_bins.cuh)
+    int tiles_x;
+    int pb_rounds, pb_min;             // camera-ray rounds per loop turn; rounds after the first need this many fresh lanes
 };
 
 // ------------------------------------------------------------------------------------------
@@ -410,6 +413,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
 }  // namespace rt
 
 #include "rt_wavefront.cuh"
+#include "rt_primary_bins.cuh"
 
 namespace rt {
 
@@ -631,6 +635,9 @@ struct rt_ctx {
     // wavefront variant: path pool
     void *wf_mem = nullptr;
     size_t wf_bytes = 0;
+    // per-tile candidate lists of the camera rays (rt_primary_bins.cuh), rebuilt by every render call
+    void *bins = nullptr;
+    size_t bins_bytes = 0;
 };
 
 constexpr int QUEUE_WORDS = 8;
@@ -949,14 +956,14 @@ int resolve_accel(const rt_ctx *ctx, int accel) {
 
 size_t trace_smem(const SceneBlob &b) { return (size_t)b.bytes + (size_t)CAND_CAP * TRACE_BLOCK * sizeof(unsigned short); }
 
-template <typename T, int ACCEL> int launch_shape(rt_ctx *ctx, size_t smem, int *grid) {
-    RT_CUDA(cudaFuncSetAttribute(trace_kernel<T, ACCEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <typename Kernel> int launch_shape(rt_ctx *ctx, Kernel kernel, size_t smem, int *grid) {
+    RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<T, ACCEL>, TRACE_BLOCK, smem));
+    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_BLOCK, smem));
     if (per_sm < 1) return RT_EINVAL;
     *grid = ctx->sm_count * per_sm;
     cudaFuncAttributes fa;
-    RT_CUDA(cudaFuncGetAttributes(&fa, trace_kernel<T, ACCEL>));
+    RT_CUDA(cudaFuncGetAttributes(&fa, kernel));
     ctx->stats.regs = fa.numRegs;
     ctx->stats.smem_bytes = (int)(smem + fa.sharedSizeBytes);
     ctx->stats.grid = *grid;
@@ -1062,10 +1069,20 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     int rc = lbvh ? build_lbvh(ctx) : RT_OK;
     if (rc) return rc;
     const bool compact = lbvh && ctx->bvh.compact;
-    rc = compact ? launch_shape<T, ACCEL_LBVH_COMPACT>(ctx, smem, &grid)
-                 : (lbvh ? launch_shape<T, RT_ACCEL_LBVH>(ctx, smem, &grid) : launch_shape<T, RT_ACCEL_LINEAR>(ctx, smem, &grid));
+    // camera rays through per-tile candidate lists (rt_primary_bins.cuh): linear scan only, same image either way
+    const bool pbins = !lbvh && o.primary_bins != RT_PBINS_OFF && !getenv("RT_NO_PBINS");
+    rc = pbins ? launch_shape(ctx, trace_kernel_pb<T>, smem, &grid)
+               : (compact ? launch_shape(ctx, trace_kernel<T, ACCEL_LBVH_COMPACT>, smem, &grid)
+                          : (lbvh ? launch_shape(ctx, trace_kernel<T, RT_ACCEL_LBVH>, smem, &grid)
+                                  : launch_shape(ctx, trace_kernel<T, RT_ACCEL_LINEAR>, smem, &grid)));
     if (rc) return rc;
     TraceArgs<T> A;
+    A.bins = nullptr;
+    A.tiles_x = 0;
+    A.pb_rounds = 3;                   // measured at config 2 (tools/tune_pbins.sh): 1 round 89-91 ms, 2 rounds 87.5-88, 3+ rounds 86.5-87
+    A.pb_min = 1;
+    if (const char *e = getenv("RT_PB_ROUNDS")) A.pb_rounds = atoi(e) > 0 ? atoi(e) : A.pb_rounds;       // tuning knobs
+    if (const char *e = getenv("RT_PB_MIN")) A.pb_min = atoi(e);
     A.bvh = ctx->bvh;
     // node visits per loop turn: about one root-to-leaf descent plus slack (measured: 16 best for 487 spheres,
     // 24 for 99 860); finished lanes are shaded between rounds
@@ -1094,7 +1111,20 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
     if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
     ctx->stats.grid = grid;
-    if (compact) trace_kernel<T, ACCEL_LBVH_COMPACT><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    if (pbins) {
+        const int tiles_x = (cam.width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (cam.height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
+        const size_t tiles = (size_t)tiles_x * tiles_y;
+        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned short));
+        if (rc) return rc;
+        A.bins = static_cast<const unsigned short *>(ctx->bins);
+        A.tiles_x = tiles_x;
+        bin_kernel<T><<<(unsigned)((tiles + 127) / 128), 128, 0, ctx->stream>>>(
+            A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n, cam.width, cam.height, tiles_x, tiles_y,
+            static_cast<unsigned short *>(ctx->bins));
+        RT_CUDA(cudaGetLastError());
+        ctx->stats.launches += 1;
+        trace_kernel_pb<T><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+    } else if (compact) trace_kernel<T, ACCEL_LBVH_COMPACT><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     else if (lbvh) trace_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     else trace_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     RT_CUDA(cudaGetLastError());
@@ -1283,6 +1313,7 @@ int rt_destroy(rt_ctx *ctx) {
     if (ctx->queue) cudaFree(ctx->queue);
     for (void *m : ctx->bvh_mem) if (m) cudaFree(m);
     if (ctx->wf_mem) cudaFree(ctx->wf_mem);
+    if (ctx->bins) cudaFree(ctx->bins);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

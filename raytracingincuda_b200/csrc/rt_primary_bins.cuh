@@ -1,0 +1,254 @@
+// rt_primary_bins.cuh -- screen-space candidate bins for PRIMARY rays, and the persistent path tracer that uses them.
+// Included by rt_kernels.cu after trace_kernel (it shares TraceArgs, camera_ray, scatter, sky, global_row).
+//
+// Why.  In the reference every ray segment pays the full hit_world scan (GF hittable.h:80-98).  A camera ray, unlike a
+// scattered one, is known before the frame starts up to its two random draws (pixel jitter, lens sample; GF camera.h:
+// 145-155): all camera rays of a 16 x 16 pixel tile lie inside a thin bundle around the tile's central ray.  A tiny kernel
+// (bin_kernel, one thread per tile, microseconds) lists, per tile, every slot that ANY ray of that bundle can touch; the
+// path tracer resolves a camera ray against its tile's list with the reference's exact arithmetic (resolve_slot) and keeps
+// the shared-memory scan for the scattered segments.  Scene 1 has 2.89 segments per path, so this removes about a third of
+// all scans.  The hit a camera ray gets is the one the full scan returns, bit for bit, because
+//   * the closest hit is order independent (rt_device.cuh: each slot contributes its first root > tmin, the minimum wins,
+//     ties go to the lowest slot), so it can be computed over any SUPERSET of the slots with a non-negative discriminant;
+//   * the list is such a superset (proof below).
+// A tile whose list would not fit (PB_CAP slots) is marked PB_OVERFLOW and its camera rays take the shared-memory scan.
+//
+// The bundle.  A camera ray joins a lens point L = centre + q0*disk_u + q1*disk_v, q0^2 + q1^2 < 1, to a point
+// Q = pixel00 + px*du + py*dv of the focus plane with |px - i| <= 0.5, |py - j| <= 0.5.  With L0 = centre and Q0 the target
+// of the tile's middle, |L - L0| <= rho (largest singular value of [disk_u disk_v]) and |Q - Q0| <= hT = hx|du| + hy|dv|
+// (hx, hy: half extents of the tile in pixels).  A point of the ray is X(s) = (1-s) L + s Q, s > 0, hence
+//   |X(s) - X0(s)| <= |1-s| rho + s hT <= rho + s (hT + rho),       X0(s) = (1-s) L0 + s Q0  (the axis).
+// The reference's float discriminant of a sphere (c, r) can only be >= 0 when the ray passes within
+//   r_eff = sqrt(r^2 + 64 * 2^-24 * D^2),  D >= |c - origin|
+// of c (its rounding error is below 18 * 2^-24 * |d|^2 |c - o|^2; 64 leaves a factor 3.5).  So a
+// slot can only matter if some axis point satisfies |X0(s) - c| <= R0 + kappa * s|a|, R0 = r_eff + rho, kappa = (hT + rho)/|a|,
+// a = Q0 - L0.  Minimising the left side minus the right side over ALL real s (a superset of s > 0) gives the closed form
+//   perp * sqrt(1 - kappa^2) - kappa * along <= R0,        along = (c - L0).a/|a|,  perp = distance of c from the axis,
+// which bin_kernel evaluates in double with absolute and relative margins that dwarf the float rounding of camera_ray
+// (|px|, |py| round monotonically, so they stay inside the tile; L and Q move by a few 1e-7 relative).
+#pragma once
+
+namespace rt {
+
+constexpr int PB_SHIFT = 4;                 // tiles of 16 x 16 pixels
+constexpr int PB_STRIDE = 32;               // uint16 per tile record: [0] = count or PB_OVERFLOW, [1..31] = slots, ascending
+constexpr int PB_CAP = PB_STRIDE - 1;
+constexpr unsigned PB_OVERFLOW = 0xffffu;
+
+template <typename T>
+__global__ void __launch_bounds__(128) bin_kernel(const __grid_constant__ DevCamera<T> cam, const typename Num<T>::vec4 *__restrict__ geom,
+                                                  int n, int width, int height, int tiles_x, int tiles_y,
+                                                  unsigned short *__restrict__ bins) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= tiles_x * tiles_y) return;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int i0 = tx << PB_SHIFT, j0 = ty << PB_SHIFT;
+    const int i1 = min(i0 + (1 << PB_SHIFT), width) - 1, j1 = min(j0 + (1 << PB_SHIFT), height) - 1;
+    const double mx = 0.5 * (i0 + i1), my = 0.5 * (j0 + j1);
+    const double hx = 0.5 * (i1 - i0) + 0.5 + 1e-3, hy = 0.5 * (j1 - j0) + 0.5 + 1e-3;
+    const double L0[3] = {(double)cam.center.x, (double)cam.center.y, (double)cam.center.z};
+    const double du[3] = {(double)cam.du.x, (double)cam.du.y, (double)cam.du.z}, dv[3] = {(double)cam.dv.x, (double)cam.dv.y, (double)cam.dv.z};
+    const double p0[3] = {(double)cam.pixel00.x, (double)cam.pixel00.y, (double)cam.pixel00.z};
+    double a[3], la2 = 0.0, lq2 = 0.0, ll2 = 0.0, ndu = 0.0, ndv = 0.0;
+    for (int q = 0; q < 3; ++q) {
+        const double Q0 = p0[q] + mx * du[q] + my * dv[q];
+        a[q] = Q0 - L0[q];
+        la2 += a[q] * a[q]; lq2 += Q0 * Q0; ll2 += L0[q] * L0[q];
+        ndu += du[q] * du[q]; ndv += dv[q] * dv[q];
+    }
+    const double la = sqrt(la2);
+    double rho = 0.0;
+    if (!(cam.defocus_angle <= T(0))) {
+        // largest singular value of the 3 x 2 matrix [disk_u disk_v]
+        double uu = 0.0, vv = 0.0, uv = 0.0;
+        const double U[3] = {(double)cam.disk_u.x, (double)cam.disk_u.y, (double)cam.disk_u.z};
+        const double V[3] = {(double)cam.disk_v.x, (double)cam.disk_v.y, (double)cam.disk_v.z};
+        for (int q = 0; q < 3; ++q) { uu += U[q] * U[q]; vv += V[q] * V[q]; uv += U[q] * V[q]; }
+        rho = sqrt(0.5 * (uu + vv + sqrt((uu - vv) * (uu - vv) + 4.0 * uv * uv))) * (1.0 + 1e-9);
+    }
+    const double margin = 1e-5 * (1.0 + sqrt(ll2) + sqrt(lq2));                   // float rounding of L and Q is ~1e-7 relative
+    const double hT = hx * sqrt(ndu) + hy * sqrt(ndv);
+    const double kappa = (hT + rho + margin) / la * (1.0 + 1e-6);
+    unsigned short *rec = bins + (size_t)tile * PB_STRIDE;
+    if (!(la > 0.0) || !(kappa < 0.5) || !(rho < 1e300) || !(margin < 1e300)) { rec[0] = (unsigned short)PB_OVERFLOW; return; }   // also NaN/inf cameras
+    const double cosk = sqrt(1.0 - kappa * kappa), inv_la = 1.0 / la;
+    int cnt = 0;
+    for (int s = 0; s < n; ++s) {
+        const typename Num<T>::vec4 g = geom[s];
+        const double b[3] = {(double)g.x - L0[0], (double)g.y - L0[1], (double)g.z - L0[2]};
+        const double r = fabs((double)g.w);
+        const double bb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+        const double along = (b[0] * a[0] + b[1] * a[1] + b[2] * a[2]) * inv_la;
+        const double perp = sqrt(fmax(bb - along * along, 0.0));
+        const double D = sqrt(bb) + rho + margin;
+        const double reff = sqrt(r * r + (64.0 * 5.9604644775390625e-08) * D * D);
+        const double R0 = reff + rho + margin;
+        const double lhs = perp * cosk, rhs = (R0 + kappa * along) * (1.0 + 1e-9) + margin;
+        if (!(lhs > rhs)) {                                                       // NaN geometry counts as a candidate
+            if (cnt < PB_CAP) rec[1 + cnt] = (unsigned short)s;
+            ++cnt;
+        }
+    }
+    rec[0] = (unsigned short)(cnt <= PB_CAP ? (unsigned)cnt : PB_OVERFLOW);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Persistent path tracer with binned camera rays (linear shared-memory scan for everything else).  Same jobs, same Philox
+// counters, same partial planes and therefore the same image, bit for bit, as trace_kernel<T, RT_ACCEL_LINEAR>.
+//
+// A lane is in one of three phases: FRESH (starts the next sample of its job), HIT (a closest hit waits to be shaded),
+// RAY (a live ray waits for the scan).  One loop turn =
+//   A  up to pb_rounds times: job fetch; FRESH lanes generate their camera ray and resolve it against the tile list --
+//      a miss adds the sky and leaves the lane FRESH for the next round, a hit makes it HIT;
+//   B  HIT lanes scatter (one Philox block, dimension depth+1) and become RAY, or end the path and become FRESH;
+//   C  one shared-memory scan for the RAY lanes; misses add the sky (FRESH), hits become HIT.
+// so (almost) every lane that enters the scan carries a scattered ray.
+template <typename T>
+__global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
+    using N = Num<T>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
+    const SceneView<T> sc = view_of<T>(smem, A.scene);
+    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
+    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene);
+
+    const int lane = threadIdx.x & 31;
+    enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
+    enum { FRESH = 0, HIT = 1, RAY = 2 };
+    int state = NEED_JOB, phase = FRESH;
+    PathState<T> ps;
+    ps.o = A.cam.center;
+    ps.d.x = T(0); ps.d.y = T(1); ps.d.z = T(0);
+    ps.att.x = ps.att.y = ps.att.z = T(1);
+    ps.puy = T(0);
+    Hit<T> hit;
+    hit.t = N::inf();
+    hit.id = -1;
+    T acc_r = T(0), acc_g = T(0), acc_b = T(0);
+    int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
+    uint32_t pixel = 0, tile = 0;
+    unsigned long long job = 0;
+    unsigned int n_seg = 0, n_path = 0;
+
+    auto end_path = [&](T cr, T cg, T cb) {
+        acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);
+        ++n_path;
+        phase = FRESH;
+        if (++sample == sample_end) {
+            typename N::vec4 v;
+            v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
+            A.partial[job] = v;
+            state = NEED_JOB;
+        }
+    };
+    auto end_in_sky = [&]() {
+        T sr, sg, sb;
+        sky<T>(ps.puy, sr, sg, sb);
+        end_path(N::mul(ps.att.x, sr), N::mul(ps.att.y, sg), N::mul(ps.att.z, sb));
+    };
+
+    for (;;) {
+        // ---- A: camera rays through the tile lists ----
+#pragma unroll 1
+        for (int round = 0; round < A.pb_rounds; ++round) {
+            const unsigned want = __ballot_sync(FULL, state == NEED_JOB);
+            if (want) {
+                const int leader = __ffs(want) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
+                base = __shfl_sync(FULL, base, leader);
+                if (state == NEED_JOB) {
+                    job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                    if (job < A.total_jobs) {
+                        const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;
+                        const unsigned long long lp = job - cl * A.pix_local;
+                        const int c = A.c_begin + (int)cl;
+                        const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
+                        pi = (int)(lp - (unsigned long long)lr * A.width);
+                        pj = global_row(A, lr);
+                        pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
+                        tile = (uint32_t)(pj >> PB_SHIFT) * (uint32_t)A.tiles_x + (uint32_t)(pi >> PB_SHIFT);
+                        sample = (int)((long long)c * A.spp / A.chunks);
+                        sample_end = (int)((long long)(c + 1) * A.spp / A.chunks);
+                        acc_r = acc_g = acc_b = T(0);
+                        state = ACTIVE;
+                        phase = FRESH;
+                    } else {
+                        state = DEAD;
+                    }
+                }
+            }
+            const bool prim = (state == ACTIVE && phase == FRESH);
+            const int n_prim = __popc(__ballot_sync(FULL, prim));
+            if (n_prim == 0 || (round > 0 && n_prim < A.pb_min)) break;
+            if (prim) {
+                Philox ph;
+                ph.open(A.keys, pixel, (uint32_t)sample, 0u);
+                ph.block(0);
+                camera_ray(A, pi, pj, ph, ps);
+                depth = 0;
+                const uint4 *rec = reinterpret_cast<const uint4 *>(A.bins) + (size_t)tile * (PB_STRIDE / 8);
+                uint4 q = __ldg(rec);
+                const unsigned cnt = q.x & 0xffffu;
+                const T a = dot3(ps.d, ps.d);
+                const bool sane = a > T(1e-30) && a < T(1e30);        // false for NaN too: such rays take the scan's exact loop
+                if (cnt == PB_OVERFLOW || !sane) {
+                    phase = RAY;                                      // this camera ray goes through the shared-memory scan
+                } else {
+                    Hit<T> h;
+                    h.t = N::inf();
+                    h.id = -1;
+#pragma unroll 1
+                    for (unsigned e = 1; e <= cnt; ++e) {
+                        // the record is consumed 16 bits at a time: shift the 128-bit window, refill every 8 entries
+                        if ((e & 7u) == 0u) q = __ldg(rec + (e >> 3));
+                        else {
+                            q.x = __funnelshift_r(q.x, q.y, 16); q.y = __funnelshift_r(q.y, q.z, 16);
+                            q.z = __funnelshift_r(q.z, q.w, 16); q.w >>= 16;
+                        }
+                        resolve_slot<T>(geo.addr, (int)(q.x & 0xffffu), ps.o, ps.d, a, h);
+                    }
+                    ++n_seg;
+                    if (h.id < 0) end_in_sky();
+                    else { hit = h; phase = HIT; }
+                }
+            }
+        }
+        if (__all_sync(FULL, state == DEAD)) break;
+
+        // ---- B: shade the pending hits (GF camera.h:92-117) ----
+        if (state == ACTIVE && phase == HIT) {
+            Philox ph;
+            ph.open(A.keys, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
+            ph.block(0);
+            const bool alive = scatter(sc, hit, ph, ps);
+            if (!alive || ++depth >= A.max_depth) end_path(T(0), T(0), T(0));     // GF camera.h:117 / :84,127 -> black
+            else phase = RAY;
+        }
+
+        // ---- C: closest hit over all slots for the scattered rays (all 32 lanes take part in the scan) ----
+        const bool scan = (state == ACTIVE && phase == RAY);
+        if (__any_sync(FULL, scan)) {
+            const Hit<T> h = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+            if (scan) {
+                ++n_seg;
+                if (h.id < 0) end_in_sky();
+                else { hit = h; phase = HIT; }
+            }
+        }
+    }
+
+    unsigned long long seg = n_seg, pth = n_path;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        seg += __shfl_xor_sync(FULL, seg, off);
+        pth += __shfl_xor_sync(FULL, pth, off);
+    }
+    if (lane == 0) {
+        atomicAdd(A.queue + 1, seg);
+        atomicAdd(A.queue + 2, pth);
+    }
+}
+
+}  // namespace rt

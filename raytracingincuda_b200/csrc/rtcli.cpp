@@ -4,7 +4,7 @@
 // Same six flags, same usage text, same exit codes, same stdout (`render_ms,e2e_ms`, both
 // setw(15) fixed setprecision(8); GF main.cu:342-343,397-398) and the same PPM naming scheme
 // (GF main.cu:349-357) with the variant prefix `b200_float_` / `b200_double_`.  Everything new
-// (--seed, --precision, --gpus, --gather, --accel, --kernel, --scaled_half, --scene_file, --dump_scene, --prefix, --no-ppm, --stats) defaults to the reference's
+// (--seed, --precision, --gpus, --gather, --accel, --kernel, --primary_bins, --scaled_half, --scene_file, --dump_scene, --prefix, --no-ppm, --stats) defaults to the reference's
 // behaviour, and extra diagnostics go to stderr so the benchmark scripts' $(...) capture of stdout
 // (global_float_benchmark.sh:53-74) stays valid.
 #include "rt_b200.h"
@@ -52,6 +52,7 @@ struct Args {
     unsigned long long seed = 1227;
     bool use_double = false, no_ppm = false, stats = false, lbvh = false, wavefront = false;
     int accel = RT_ACCEL_LINEAR;
+    int primary_bins = RT_PBINS_AUTO;
     int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix, gather = "p2p";
     std::string scene_file, dump_scene;     // general scene loader (float): read the slots from / write them to a text file
@@ -81,7 +82,7 @@ Args parse(int argc, char **argv) {
         if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); has_value = true; }
         const bool flag_only = (name == "no-ppm" || name == "stats");
         static const char *known[] = {"scene_id", "width", "height", "samples", "bounces", "threads", "seed",
-                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel", "gather", "scene_file", "dump_scene"};
+                                      "precision", "gpus", "split", "prefix", "no-ppm", "stats", "accel", "scaled_half", "kernel", "gather", "scene_file", "dump_scene", "primary_bins"};
         bool ok = false;
         for (const char *n : known) ok = ok || name == n;
         if (!ok) die_like_cxxopts("no_such_option", "Option '" + name + "' does not exist");
@@ -105,6 +106,7 @@ Args parse(int argc, char **argv) {
         else if (name == "dump_scene") a.dump_scene = value;
         else if (name == "accel") { a.lbvh = (value == "lbvh"); a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : RT_ACCEL_LINEAR); }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
+        else if (name == "primary_bins") a.primary_bins = (value == "off") ? RT_PBINS_OFF : RT_PBINS_ON;
         else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
         else if (name == "no-ppm") a.no_ppm = true;
         else if (name == "stats") a.stats = true;
@@ -206,6 +208,7 @@ int main(int argc, char **argv) {
             o.seed = a.seed;
             o.threads = a.threads;
             o.accel = a.accel;
+            o.primary_bins = a.primary_bins;
             o.kernel = a.wavefront ? RT_KERNEL_WAVEFRONT : RT_KERNEL_MEGA;
             if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; o.place_rows = p2p ? 1 : 0; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;

@@ -328,6 +328,63 @@ def test_scene_outside_the_filter_range_takes_the_exact_scan(renderer):
     assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
 
 
+# ------------------------------------------------ camera rays through per-tile candidate lists ------
+@pytest.mark.parametrize("scene_id,w,h,spp,depth,double", [(1, 320, 192, 8, 25, False), (2, 200, 120, 8, 50, False),
+                                                            (3, 97, 61, 12, 50, False), (1, 64, 40, 6, 25, True)])
+def test_primary_bins_equal_the_full_scan(renderer, scene_id, w, h, spp, depth, double):
+    """rt_opts.primary_bins: a camera ray resolved against its tile's candidate list gets the hit the shared-memory scan
+    returns, so the frames are identical bit for bit -- and equal to the oracle's (which has no bins at all)."""
+    renderer.upload_scene(rt.scene(scene_id, double=double))
+    cam = rt.camera(w, h, spp, depth, double=double)
+    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
+    st_on = renderer.stats()
+    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    st_off = renderer.stats()
+    assert st_on.launches == st_off.launches + 1, "the bin kernel did not run"
+    assert (st_on.paths, st_on.segments) == (st_off.paths, st_off.segments)
+    assert np.array_equal(bits(on), bits(off))
+    if w * h * spp <= 200 * 120 * 8:
+        ref, seg = O.render(O.scene(scene_id, double), O.camera(w, h, spp, depth, double=double))
+        assert st_on.segments == seg
+        assert np.array_equal(bits(on), bits(ref))
+
+
+@pytest.mark.parametrize("name", ["shifted", "tiny", "huge", "concentric"])
+def test_primary_bins_on_awkward_scenes(renderer, name):
+    """Far from the origin, millimetre-sized (every slot lands in one tile: the list overflows and the tile's camera
+    rays take the scan), 4096x, and 64 nested shells (more candidates than a list holds)."""
+    slots = AUDIT_SCENES[name]()
+    renderer.upload_scene(slots)
+    cam = rt.camera(160, 96, 4, 10)
+    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
+    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    assert np.array_equal(bits(on), bits(off))
+
+
+def test_primary_bins_row_split_and_partial_tiles(renderer):
+    """Tiles are addressed by GLOBAL pixel coordinates: a row-split rank looks up the same lists; 70 rows and 100
+    columns leave partial tiles at both edges."""
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(100, 70, 8, 25)
+    whole = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    out = np.zeros_like(whole)
+    for rank in range(3):
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=3, tile_rows=2, primary_bins=api.PBINS_ON)
+        out[rt.partition_rows(cam.height, 2, rank, 3)] = renderer.render(cam, o)
+    assert np.array_equal(bits(out), bits(whole))
+
+
+def test_primary_bins_full_size_frame(renderer):
+    """BASELINE config 4's frame (3840x2160, 32 400 tiles, 33 million camera rays at 4 spp): bins on == bins off."""
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(3840, 2160, 4, 50)
+    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
+    seg_on = renderer.stats().segments
+    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    assert renderer.stats().segments == seg_on
+    assert np.array_equal(bits(on), bits(off))
+
+
 # ------------------------------------------------------------------ LBVH (RT_ACCEL_LBVH) ------
 @pytest.mark.parametrize("scene_id", [1, 2, 3])
 def test_lbvh_primary_equals_linear_scan(renderer, scene_id):

@@ -5,13 +5,16 @@
 //   v10   conservative filter, scalar: 8 FFMA + LDS.128 + SHF
 //   p8    conservative filter, packed: 7 FFMA2 + FADD2 per PAIR, 2 LDS.128, 2 SHF
 //   p7    conservative filter, packed: 7 FFMA2 per pair, 2 LDS.128, 2 FSETP, 2 predicated OR
-//   ffma / ffma2  pure FMA streams (pipe peak check)
+//   hB    half-precision projected-distance filter: 8 HFMA2 + HSET2 + LOP3 per PAIR of slots (one ray per lane), LDS.128 per pair
+//   hA    the same with two rays per lane (slot scalars broadcast by operand swizzle), LDS.128 per two slots = four tests
+//   ffma / ffma2 / hfma2 / hfma2v  pure FMA streams (pipe peak check; hfma2v = three varying register operands)
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ubench_scan ubench_scan.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("cuda error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
@@ -155,6 +158,55 @@ __global__ void __launch_bounds__(256, 4) scan_kernel(const float4 *scene, float
                 if (MODE == 8) { sA = ~sA; sB = ~sB; }
                 if (sA | sB) found += __popc(sA) + __popc(sB);
             }
+        } else if (MODE == 10 || MODE == 11) {
+            // projected distance in half2: a = c.u - o.u, b = c.v - o.v, s = a^2 + b^2 - r^2 <= thr
+            const __half2 ux = __floats2half2_rn(dy, MODE == 11 ? dz : dy), uy = __floats2half2_rn(-dx, MODE == 11 ? 0.1f : -dx), uz = __floats2half2_rn(0.f, MODE == 11 ? -dx : 0.f);
+            const __half2 vx = __floats2half2_rn(dz * dx, dz * dx), vy = __floats2half2_rn(dz * dy, dz * dy), vz = __floats2half2_rn(-dx * dx - dy * dy, -dx * dx - dy * dy);
+            const __half2 nou = __floats2half2_rn(-(ox * dy - oy * dx), -(ox * dy - oy * dx) + (MODE == 11 ? 0.3f : 0.f));
+            const __half2 nov = __floats2half2_rn(-(ox * dz * dx + oy * dz * dy), -(ox * dz * dx + oy * dz * dy));
+            const __half2 thr = __floats2half2_rn(0.02f, 0.02f);
+            const uint32_t hbase = base;
+            constexpr int TESTS_PER_LDS = (MODE == 10) ? 2 : 4;
+            for (int b = 0; b < NS / 2 / 16; ++b) {                       // 16 tests per ray and block (MODE 11: each lane scans half of the slots)
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 32 / TESTS_PER_LDS; ++k) {
+                    uint4 q;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(hbase + (b * (32 / TESTS_PER_LDS) + k) * 16));
+#pragma unroll
+                    for (int j = 0; j < (MODE == 10 ? 1 : 2); ++j) {
+                        __half2 cx, cy, cz, nr2;
+                        if (MODE == 10) {
+                            cx = *reinterpret_cast<__half2 *>(&q.x); cy = *reinterpret_cast<__half2 *>(&q.y);
+                            cz = *reinterpret_cast<__half2 *>(&q.z); nr2 = *reinterpret_cast<__half2 *>(&q.w);
+                        } else {
+                            const __half2 xy = *reinterpret_cast<__half2 *>(j ? &q.z : &q.x), zr = *reinterpret_cast<__half2 *>(j ? &q.w : &q.y);
+                            cx = __low2half2(xy); cy = __high2half2(xy); cz = __low2half2(zr); nr2 = __high2half2(zr);
+                        }
+                        __half2 a = __hfma2(cz, uz, nou); a = __hfma2(cy, uy, a); a = __hfma2(cx, ux, a);
+                        __half2 bb = __hfma2(cz, vz, nov); bb = __hfma2(cy, vy, bb); bb = __hfma2(cx, vx, bb);
+                        __half2 sres = __hfma2(a, a, nr2); sres = __hfma2(bb, bb, sres);
+                        const unsigned m = __hle2_mask(sres, thr);
+                        acc |= m & (0x00010001u << ((MODE == 10) ? k : (2 * k + j)));
+                    }
+                }
+                if (acc) found += __popc(acc);
+            }
+        } else if (MODE == 12 || MODE == 13) {
+            __half2 x0 = __floats2half2_rn(ox, oy), x1 = __floats2half2_rn(oz, dx), x2 = __floats2half2_rn(dy, dz), x3 = __floats2half2_rn(ox + 1.f, oy + 1.f);
+            __half2 x4 = __floats2half2_rn(oy, ox), x5 = __floats2half2_rn(dx, oz), x6 = __floats2half2_rn(dz, dy), x7 = __floats2half2_rn(ox - 1.f, oy - 1.f);
+            const __half2 m = __floats2half2_rn(dx, dx), c = __floats2half2_rn(dy, dz);
+#pragma unroll 1
+            for (int it = 0; it < NS; ++it) {
+                if (MODE == 12) {
+                    x0 = __hfma2(x0, m, c); x1 = __hfma2(x1, m, c); x2 = __hfma2(x2, m, c); x3 = __hfma2(x3, m, c);
+                    x4 = __hfma2(x4, m, c); x5 = __hfma2(x5, m, c); x6 = __hfma2(x6, m, c); x7 = __hfma2(x7, m, c);
+                } else {
+                    x0 = __hfma2(x0, x3, x5); x1 = __hfma2(x1, x4, x6); x2 = __hfma2(x2, x5, x7); x3 = __hfma2(x3, x6, x0);
+                    x4 = __hfma2(x4, x7, x1); x5 = __hfma2(x5, x0, x2); x6 = __hfma2(x6, x1, x3); x7 = __hfma2(x7, x2, x4);
+                }
+            }
+            accum += __low2float(x0) + __high2float(x1) + __low2float(x2) + __high2float(x3) + __low2float(x4) + __high2float(x5) + __low2float(x6) + __high2float(x7);
         } else if (MODE == 4) {
             float x0 = ox, x1 = oy, x2 = oz, x3 = dx, x4 = dy, x5 = dz, x6 = ox + 1.f, x7 = oy + 1.f;
 #pragma unroll 1
@@ -228,6 +280,20 @@ int main() {
         hp[i] = make_float4(hf[i].x, hf[i + 1].x, hf[i].y, hf[i + 1].y);
         hp[i + 1] = make_float4(hf[i].z, hf[i + 1].z, hf[i].w, hf[i + 1].w);
     }
+    // half-precision records: hB = (cx_a,cx_b)(cy_a,cy_b)(cz_a,cz_b)(-r2_a,-r2_b) per slot pair; hA = (cx,cy)(cz,-r2) per slot
+    std::vector<__half2> hb(2 * NS), ha(2 * NS);
+    for (int i = 0; i < NS; i += 2) {
+        hb[2 * i + 0] = __floats2half2_rn(h[i].x, h[i + 1].x); hb[2 * i + 1] = __floats2half2_rn(h[i].y, h[i + 1].y);
+        hb[2 * i + 2] = __floats2half2_rn(h[i].z, h[i + 1].z); hb[2 * i + 3] = __floats2half2_rn(-h[i].w * h[i].w, -h[i + 1].w * h[i + 1].w);
+    }
+    for (int i = 0; i < NS; ++i) { ha[2 * i] = __floats2half2_rn(h[i].x, h[i].y); ha[2 * i + 1] = __floats2half2_rn(h[i].z, -h[i].w * h[i].w); }
+    float4 *scene_hb, *scene_ha;
+    CK(cudaMalloc(&scene_hb, sizeof(float4) * NS));
+    CK(cudaMalloc(&scene_ha, sizeof(float4) * NS));
+    CK(cudaMemset(scene_hb, 0, sizeof(float4) * NS));
+    CK(cudaMemset(scene_ha, 0, sizeof(float4) * NS));
+    CK(cudaMemcpy(scene_hb, hb.data(), sizeof(__half2) * 2 * NS, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(scene_ha, ha.data(), sizeof(__half2) * 2 * NS, cudaMemcpyHostToDevice));
     float4 *scene_f, *scene_p;
     CK(cudaMalloc(&scene_f, sizeof(float4) * NS));
     CK(cudaMalloc(&scene_p, sizeof(float4) * NS));
@@ -247,6 +313,10 @@ int main() {
     run<7>("r2p16", scene_f, out, cnt, sms, mhz, NS);
     run<8>("r2s32", scene_f, out, cnt, sms, mhz, NS);
     run<9>("r2p16c", scene_f, out, cnt, sms, mhz, NS);
+    run<10>("hB", scene_hb, out, cnt, sms, mhz, NS);
+    run<11>("hA", scene_ha, out, cnt, sms, mhz, NS);
+    run<12>("hfma2", scene, out, cnt, sms, mhz, NS * 8.0);
+    run<13>("hfma2v", scene, out, cnt, sms, mhz, NS * 8.0);
     run<4>("ffma", scene, out, cnt, sms, mhz, NS * 8.0);
     run<5>("ffma2", scene, out, cnt, sms, mhz, NS * 8.0);
     return 0;
