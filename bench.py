@@ -296,13 +296,13 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device=device) if rank == 0 else None
-    trace_ms, launches, segs, tests, nodes = [], [0], [0], [0], [0]
+    trace_ms, launches, segs, tests, nodes, binned = [], [0], [0], [0], [0], [0]
 
     def note_stats():
         st = r.stats()
         trace_ms.append(st.trace_ms)
         launches[0] += st.launches
-        segs[0], tests[0], nodes[0] = st.segments, st.sphere_tests, st.node_visits
+        segs[0], tests[0], nodes[0], binned[0] = st.segments, st.sphere_tests, st.node_visits, st.binned_segments
         return st
 
     def step_device():
@@ -369,12 +369,12 @@ def run_b200_arm(args):
     e2e_s = time.perf_counter() - t0
 
     t = torch.tensor([ms, e2e_s * 1e3, step_trace_ms], dtype=torch.float64, device=device)
-    seg_t = torch.tensor([segments, tests[0], nodes[0]], dtype=torch.int64, device=device)
+    seg_t = torch.tensor([segments, tests[0], nodes[0], binned[0]], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(seg_t, op=dist.ReduceOp.SUM)
     ms, e2e_ms, step_trace_ms = [float(x) for x in t.tolist()]
-    segments, sphere_tests, node_visits = [int(x) for x in seg_t.tolist()]
+    segments, sphere_tests, node_visits, binned_segments = [int(x) for x in seg_t.tolist()]
 
     line = None
     if rank == 0:
@@ -409,7 +409,8 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload),
-                       "implementation": f"float, {'on-GPU LBVH' if lbvh else 'linear scan in shared memory'}",
+                       "implementation": "float, " + ("on-GPU LBVH" if lbvh else "linear scan in shared memory, camera rays "
+                                                           "through per-tile candidate lists (rt_opts.primary_bins)"),
                        "l2": "inputs regenerate per step; "
                                    f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else "nccl-gather"))) if world > 1 else "none",
                        "chunks": chunks, "seed": 1227},
@@ -418,15 +419,18 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
             "gpu_launches": timed_launches,
             "clocks": clk,
-            "roofline": roof if lbvh else {"bound": "fp32", "kernel": "trace_kernel<float,linear>", "achieved": round(achieved, 3),
+            "roofline": roof if lbvh else {"bound": "fp32", "kernel": "trace_kernel_pb<float>", "achieved": round(achieved, 3),
                          "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                          "frac_at_observed_clock": round(achieved / (peak * obs / sm_max), 4),
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks_src} MEASURED_PEAKS.json)",
                          "algorithmic": (f"{sphere_tests} sphere tests x {FLOP_PER_TEST} FLOP per step ({node_visits} BVH node "
                                          f"visits not counted)" if lbvh else
                                          f"{segments} segments x {n_slots} slots x {FLOP_PER_TEST} FLOP per step"),
-                         "note": ("achieved counts the reference's arithmetic (18 FLOP per (ray, slot) test); the kernel itself runs a "
-                                  "7-FMA conservative filter per test and the exact test on the ~0.5 % candidates"),
+                         "note": ("achieved counts the reference's arithmetic (18 FLOP per (ray, slot) test of every segment, SURVEY 8d); "
+                                  f"the kernel resolves the {binned_segments} camera-ray segments against per-tile candidate lists "
+                                  f"and scans the other {segments - binned_segments} with a 7-FMA conservative filter per test plus "
+                                  "the exact test on the ~0.5 % candidates"),
+                         "scanned_fraction": round((segments - binned_segments) / max(1, segments), 4),
                          "kernel_ms": round(step_trace_ms, 3), "traffic": None},
         }
         # DRAM bytes per trace_kernel launch from the committed ncu pass over this same command
@@ -443,7 +447,17 @@ def run_b200_arm(args):
             pass
         st = r.stats()
         line["kernel"] = {"grid": st.grid, "block": st.block, "regs": st.regs, "smem_bytes": st.smem_bytes,
-                          "segments_per_path": round(segments / paths, 4)}
+                          "segments_per_path": round(segments / paths, 4),
+                          "binned_segments_per_path": round(binned_segments / paths, 4)}
+        if world == 1 and not lbvh and not args.no_lbvh_extra:
+            # the same workload with every segment through the shared-memory scan (rt_opts.primary_bins off): same image
+            oo = api.make_opts(primary_bins=api.PBINS_OFF)
+            r.render(cam, oo, out=frame_dev)
+            r.render(cam, oo, out=frame_dev)
+            so = r.stats()
+            line["scan_every_segment"] = {"value": round(paths / (so.render_ms * 1e-3) / 1e6, 3), "unit": METRIC,
+                                          "ms_per_step": round(so.render_ms, 3), "kernel": "trace_kernel<float,linear>",
+                                          "roofline_frac": round(so.segments * n_slots * FLOP_PER_TEST / (so.trace_ms * 1e-3) / 1e12 / peak, 4)}
         if world == 1 and not lbvh and n_slots >= 256 and not args.no_lbvh_extra:
             # the same workload through the on-GPU LBVH (bit-identical image): informative, not the headline
             ob = api.make_opts(accel=api.ACCEL_LBVH)

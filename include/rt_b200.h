@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 enum {
     RT_OK = 0,
@@ -112,6 +112,8 @@ typedef struct rt_stats {
     int32_t chunks;          /* accumulation chunks of the last call */
     int32_t grid, block;     /* launch shape of the path-tracing kernel */
     int32_t regs, smem_bytes;
+    uint64_t binned_segments; /* camera-ray segments resolved against their tile's candidate list instead of the scan
+                               * (rt_opts.primary_bins); they are included in `segments` */
 } rt_stats;
 
 /* ------------------------------------------------------------------ host side (no GPU) ---- */

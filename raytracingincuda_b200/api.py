@@ -56,7 +56,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("node_visits", C.c_uint64), ("render_ms", C.c_float), ("trace_ms", C.c_float),
                 ("launches", C.c_int32), ("chunks", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
-                ("regs", C.c_int32), ("smem_bytes", C.c_int32)]
+                ("regs", C.c_int32), ("smem_bytes", C.c_int32), ("binned_segments", C.c_uint64)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)

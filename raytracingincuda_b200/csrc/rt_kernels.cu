@@ -54,11 +54,11 @@ template <typename T> struct TraceArgs {
     unsigned long long magic_pix;      // floor(2^64 / pix_local) + 1: job / pix_local == umul64hi(job, magic_pix)
     unsigned long long magic_width;    // floor(2^64 / width) + 1
     typename Num<T>::vec4 *partial;    // [job]
-    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests
+    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests, [5] binned camera segments
     BvhView bvh;                       // RT_ACCEL_LBVH only
     int bvh_steps;                     // at most this many node visits per loop turn ...
     int bvh_min_active;                // ... and the round ends once fewer lanes than this are still traversing
-    const unsigned short *bins;        // trace_kernel_pb only: per-tile candidate lists of the camera rays (rt_primary_bins.cuh)
+    const unsigned int *bins;          // trace_kernel_pb only: per-tile candidate lists of the camera rays (rt_primary_bins.cuh)
     int tiles_x;
     int pb_rounds, pb_min;             // camera-ray rounds per loop turn; rounds after the first need this many fresh lanes
 };
@@ -1056,6 +1056,21 @@ int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_loca
     return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
 }
 
+// The LBVH is a float structure: these helpers keep the double instantiation of trace() from naming float-only kernels
+// (trace() rejects double + LBVH before it gets here).
+inline void launch_bins_bvh(const DevCamera<float> &cam, const BvhView &bv, int w, int h, int tx, int ty, unsigned int *bins, unsigned grid,
+                            cudaStream_t st) {
+    bin_kernel_bvh<<<grid, 128, 0, st>>>(cam, bv, w, h, tx, ty, bins);
+}
+inline void launch_bins_bvh(const DevCamera<double> &, const BvhView &, int, int, int, int, unsigned int *, unsigned, cudaStream_t) {}
+template <typename T, int ACCEL> void launch_pb(const TraceArgs<T> &A, int grid, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR) trace_kernel_pb<T, ACCEL><<<grid, TRACE_BLOCK, smem, st>>>(A);
+}
+template <typename T, int ACCEL> int shape_pb(rt_ctx *ctx, size_t smem, int *grid) {
+    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR) return launch_shape(ctx, trace_kernel_pb<T, ACCEL>, smem, grid);
+    else return RT_EPRECISION;
+}
+
 // Launches the path tracer for chunks [c0,c1) over `rows_local` rows into `partial`.
 template <typename T, typename Cam>
 int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
@@ -1069,12 +1084,13 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     int rc = lbvh ? build_lbvh(ctx) : RT_OK;
     if (rc) return rc;
     const bool compact = lbvh && ctx->bvh.compact;
-    // camera rays through per-tile candidate lists (rt_primary_bins.cuh): linear scan only, same image either way
-    const bool pbins = !lbvh && o.primary_bins != RT_PBINS_OFF && !getenv("RT_NO_PBINS");
-    rc = pbins ? launch_shape(ctx, trace_kernel_pb<T>, smem, &grid)
-               : (compact ? launch_shape(ctx, trace_kernel<T, ACCEL_LBVH_COMPACT>, smem, &grid)
-                          : (lbvh ? launch_shape(ctx, trace_kernel<T, RT_ACCEL_LBVH>, smem, &grid)
-                                  : launch_shape(ctx, trace_kernel<T, RT_ACCEL_LINEAR>, smem, &grid)));
+    // camera rays through per-tile candidate lists (rt_primary_bins.cuh): same image either way
+    const bool pbins = o.primary_bins != RT_PBINS_OFF && !getenv("RT_NO_PBINS");
+    if (pbins) rc = compact ? shape_pb<T, ACCEL_LBVH_COMPACT>(ctx, smem, &grid)
+                            : (lbvh ? shape_pb<T, RT_ACCEL_LBVH>(ctx, smem, &grid) : shape_pb<T, RT_ACCEL_LINEAR>(ctx, smem, &grid));
+    else rc = compact ? launch_shape(ctx, trace_kernel<T, ACCEL_LBVH_COMPACT>, smem, &grid)
+                      : (lbvh ? launch_shape(ctx, trace_kernel<T, RT_ACCEL_LBVH>, smem, &grid)
+                              : launch_shape(ctx, trace_kernel<T, RT_ACCEL_LINEAR>, smem, &grid));
     if (rc) return rc;
     TraceArgs<T> A;
     A.bins = nullptr;
@@ -1114,16 +1130,20 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     if (pbins) {
         const int tiles_x = (cam.width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (cam.height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
         const size_t tiles = (size_t)tiles_x * tiles_y;
-        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned short));
+        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned int));
         if (rc) return rc;
-        A.bins = static_cast<const unsigned short *>(ctx->bins);
+        unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
+        A.bins = bins;
         A.tiles_x = tiles_x;
-        bin_kernel<T><<<(unsigned)((tiles + 127) / 128), 128, 0, ctx->stream>>>(
-            A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n, cam.width, cam.height, tiles_x, tiles_y,
-            static_cast<unsigned short *>(ctx->bins));
+        const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
+        if (lbvh) launch_bins_bvh(A.cam, ctx->bvh, cam.width, cam.height, tiles_x, tiles_y, bins, bin_grid, ctx->stream);
+        else bin_kernel<T><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n,
+                                                             cam.width, cam.height, tiles_x, tiles_y, bins);
         RT_CUDA(cudaGetLastError());
         ctx->stats.launches += 1;
-        trace_kernel_pb<T><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
+        if (compact) launch_pb<T, ACCEL_LBVH_COMPACT>(A, grid, smem, ctx->stream);
+        else if (lbvh) launch_pb<T, RT_ACCEL_LBVH>(A, grid, smem, ctx->stream);
+        else launch_pb<T, RT_ACCEL_LINEAR>(A, grid, smem, ctx->stream);
     } else if (compact) trace_kernel<T, ACCEL_LBVH_COMPACT><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     else if (lbvh) trace_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
     else trace_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(A);
@@ -1162,6 +1182,7 @@ int read_counters(rt_ctx *ctx, float ms_total, float ms_trace, int chunks) {
     ctx->stats.paths = h[2];
     ctx->stats.sphere_tests = h[3] || h[4] ? h[4] : h[1] * (unsigned long long)ctx->blob.n;
     ctx->stats.node_visits = h[3];
+    ctx->stats.binned_segments = h[5];
     ctx->stats.render_ms = ms_total;
     ctx->stats.trace_ms = ms_trace;
     ctx->stats.chunks = chunks;

@@ -12,6 +12,9 @@
 //     ties go to the lowest slot), so it can be computed over any SUPERSET of the slots with a non-negative discriminant;
 //   * the list is such a superset (proof below).
 // A tile whose list would not fit (PB_CAP slots) is marked PB_OVERFLOW and its camera rays take the shared-memory scan.
+// LBVH scenes get the same lists from bin_kernel_bvh, which walks the tree with the bundle instead of looping over the
+// slots (a node's box is replaced by its bounding ball, inflated like a sphere below it), and trace_kernel_pb<float, LBVH>
+// keeps the resumable traversal for the scattered segments.
 //
 // The bundle.  A camera ray joins a lens point L = centre + q0*disk_u + q1*disk_v, q0^2 + q1^2 < 1, to a point
 // Q = pixel00 + px*du + py*dv of the focus plane with |px - i| <= 0.5, |py - j| <= 0.5.  With L0 = centre and Q0 the target
@@ -31,91 +34,180 @@
 namespace rt {
 
 constexpr int PB_SHIFT = 4;                 // tiles of 16 x 16 pixels
-constexpr int PB_STRIDE = 32;               // uint16 per tile record: [0] = count or PB_OVERFLOW, [1..31] = slots, ascending
+constexpr int PB_STRIDE = 32;               // uint32 per tile record: [0] = count or PB_OVERFLOW, [1..31] = slots
 constexpr int PB_CAP = PB_STRIDE - 1;
-constexpr unsigned PB_OVERFLOW = 0xffffu;
+constexpr unsigned PB_OVERFLOW = 0xffffffffu;
+constexpr double PB_NOISE = 64.0 * 5.9604644775390625e-08;      // 64 * 2^-24, see above
+
+// The bundle of a tile's camera rays: axis L0 + s*a, opening kappa, start radius rho (+ margins), all in double.
+struct PbBundle {
+    double L0[3], ah[3];        // lens centre, unit axis
+    double kappa, cosk, rho, margin;
+    bool ok;                    // false: degenerate camera or a very wide tile -> PB_OVERFLOW
+};
 
 template <typename T>
-__global__ void __launch_bounds__(128) bin_kernel(const __grid_constant__ DevCamera<T> cam, const typename Num<T>::vec4 *__restrict__ geom,
-                                                  int n, int width, int height, int tiles_x, int tiles_y,
-                                                  unsigned short *__restrict__ bins) {
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= tiles_x * tiles_y) return;
+__device__ __forceinline__ PbBundle pb_bundle(const DevCamera<T> &cam, int tile, int tiles_x, int width, int height) {
+    PbBundle B;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int i0 = tx << PB_SHIFT, j0 = ty << PB_SHIFT;
     const int i1 = min(i0 + (1 << PB_SHIFT), width) - 1, j1 = min(j0 + (1 << PB_SHIFT), height) - 1;
     const double mx = 0.5 * (i0 + i1), my = 0.5 * (j0 + j1);
     const double hx = 0.5 * (i1 - i0) + 0.5 + 1e-3, hy = 0.5 * (j1 - j0) + 0.5 + 1e-3;
-    const double L0[3] = {(double)cam.center.x, (double)cam.center.y, (double)cam.center.z};
+    B.L0[0] = (double)cam.center.x; B.L0[1] = (double)cam.center.y; B.L0[2] = (double)cam.center.z;
     const double du[3] = {(double)cam.du.x, (double)cam.du.y, (double)cam.du.z}, dv[3] = {(double)cam.dv.x, (double)cam.dv.y, (double)cam.dv.z};
     const double p0[3] = {(double)cam.pixel00.x, (double)cam.pixel00.y, (double)cam.pixel00.z};
     double a[3], la2 = 0.0, lq2 = 0.0, ll2 = 0.0, ndu = 0.0, ndv = 0.0;
     for (int q = 0; q < 3; ++q) {
         const double Q0 = p0[q] + mx * du[q] + my * dv[q];
-        a[q] = Q0 - L0[q];
-        la2 += a[q] * a[q]; lq2 += Q0 * Q0; ll2 += L0[q] * L0[q];
+        a[q] = Q0 - B.L0[q];
+        la2 += a[q] * a[q]; lq2 += Q0 * Q0; ll2 += B.L0[q] * B.L0[q];
         ndu += du[q] * du[q]; ndv += dv[q] * dv[q];
     }
     const double la = sqrt(la2);
-    double rho = 0.0;
+    B.rho = 0.0;
     if (!(cam.defocus_angle <= T(0))) {
         // largest singular value of the 3 x 2 matrix [disk_u disk_v]
         double uu = 0.0, vv = 0.0, uv = 0.0;
         const double U[3] = {(double)cam.disk_u.x, (double)cam.disk_u.y, (double)cam.disk_u.z};
         const double V[3] = {(double)cam.disk_v.x, (double)cam.disk_v.y, (double)cam.disk_v.z};
         for (int q = 0; q < 3; ++q) { uu += U[q] * U[q]; vv += V[q] * V[q]; uv += U[q] * V[q]; }
-        rho = sqrt(0.5 * (uu + vv + sqrt((uu - vv) * (uu - vv) + 4.0 * uv * uv))) * (1.0 + 1e-9);
+        B.rho = sqrt(0.5 * (uu + vv + sqrt((uu - vv) * (uu - vv) + 4.0 * uv * uv))) * (1.0 + 1e-9);
     }
-    const double margin = 1e-5 * (1.0 + sqrt(ll2) + sqrt(lq2));                   // float rounding of L and Q is ~1e-7 relative
+    B.margin = 1e-5 * (1.0 + sqrt(ll2) + sqrt(lq2));                              // float rounding of L and Q is ~1e-7 relative
     const double hT = hx * sqrt(ndu) + hy * sqrt(ndv);
-    const double kappa = (hT + rho + margin) / la * (1.0 + 1e-6);
-    unsigned short *rec = bins + (size_t)tile * PB_STRIDE;
-    if (!(la > 0.0) || !(kappa < 0.5) || !(rho < 1e300) || !(margin < 1e300)) { rec[0] = (unsigned short)PB_OVERFLOW; return; }   // also NaN/inf cameras
-    const double cosk = sqrt(1.0 - kappa * kappa), inv_la = 1.0 / la;
+    B.kappa = (hT + B.rho + B.margin) / la * (1.0 + 1e-6);
+    B.ok = (la > 0.0) && (B.kappa < 0.5) && (B.rho < 1e300) && (B.margin < 1e300);   // false for NaN/inf cameras too
+    B.cosk = B.ok ? sqrt(1.0 - B.kappa * B.kappa) : 0.0;
+    const double inv_la = B.ok ? 1.0 / la : 0.0;
+    for (int q = 0; q < 3; ++q) B.ah[q] = a[q] * inv_la;
+    return B;
+}
+
+// Can a ray of the bundle come within `reach(D)` of the point c?  `radius` and `rmin` describe what sits at c: a sphere
+// (radius = rmin = r) or the bounding ball of a BVH box (radius = half diagonal, rmin = smallest sphere radius inside);
+// the float-noise inflation sqrt(rmin^2 + PB_NOISE * D^2) - rmin is evaluated at a distance bound D that covers the whole ball.
+__device__ __forceinline__ bool pb_touches(const PbBundle &B, double cx, double cy, double cz, double radius, double rmin) {
+    const double b[3] = {cx - B.L0[0], cy - B.L0[1], cz - B.L0[2]};
+    const double bb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    const double along = b[0] * B.ah[0] + b[1] * B.ah[1] + b[2] * B.ah[2];
+    const double perp = sqrt(fmax(bb - along * along, 0.0));
+    const double D = sqrt(bb) + radius + B.rho + B.margin;
+    const double reach = radius + (sqrt(rmin * rmin + PB_NOISE * D * D) - rmin);
+    const double R0 = reach + B.rho + B.margin;
+    const double lhs = perp * B.cosk, rhs = (R0 + B.kappa * along) * (1.0 + 1e-9) + B.margin;
+    return !(lhs > rhs);                                                          // NaN geometry counts as a candidate
+}
+
+// one thread per tile, every slot of the scene (linear-scan scenes: a few hundred to a few thousand slots)
+template <typename T>
+__global__ void __launch_bounds__(128) bin_kernel(const __grid_constant__ DevCamera<T> cam, const typename Num<T>::vec4 *__restrict__ geom,
+                                                  int n, int width, int height, int tiles_x, int tiles_y,
+                                                  unsigned int *__restrict__ bins) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= tiles_x * tiles_y) return;
+    const PbBundle B = pb_bundle(cam, tile, tiles_x, width, height);
+    unsigned int *rec = bins + (size_t)tile * PB_STRIDE;
+    if (!B.ok) { rec[0] = PB_OVERFLOW; return; }
     int cnt = 0;
     for (int s = 0; s < n; ++s) {
         const typename Num<T>::vec4 g = geom[s];
-        const double b[3] = {(double)g.x - L0[0], (double)g.y - L0[1], (double)g.z - L0[2]};
         const double r = fabs((double)g.w);
-        const double bb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
-        const double along = (b[0] * a[0] + b[1] * a[1] + b[2] * a[2]) * inv_la;
-        const double perp = sqrt(fmax(bb - along * along, 0.0));
-        const double D = sqrt(bb) + rho + margin;
-        const double reff = sqrt(r * r + (64.0 * 5.9604644775390625e-08) * D * D);
-        const double R0 = reff + rho + margin;
-        const double lhs = perp * cosk, rhs = (R0 + kappa * along) * (1.0 + 1e-9) + margin;
-        if (!(lhs > rhs)) {                                                       // NaN geometry counts as a candidate
-            if (cnt < PB_CAP) rec[1 + cnt] = (unsigned short)s;
+        if (pb_touches(B, (double)g.x, (double)g.y, (double)g.z, r, r)) {
+            if (cnt < PB_CAP) rec[1 + cnt] = (unsigned int)s;
             ++cnt;
         }
     }
-    rec[0] = (unsigned short)(cnt <= PB_CAP ? (unsigned)cnt : PB_OVERFLOW);
+    rec[0] = cnt <= PB_CAP ? (unsigned int)cnt : PB_OVERFLOW;
+}
+
+// one thread per tile, the bundle walks the LBVH (node records of rt_lbvh.cuh); spheres outside the tree are tested directly
+__global__ void __launch_bounds__(128) bin_kernel_bvh(const __grid_constant__ DevCamera<float> cam, const __grid_constant__ BvhView bv,
+                                                      int width, int height, int tiles_x, int tiles_y, unsigned int *__restrict__ bins) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= tiles_x * tiles_y) return;
+    const PbBundle B = pb_bundle(cam, tile, tiles_x, width, height);
+    unsigned int *rec = bins + (size_t)tile * PB_STRIDE;
+    if (!B.ok) { rec[0] = PB_OVERFLOW; return; }
+    int cnt = 0;
+    auto sphere = [&](const float4 g, int slot) {
+        const double r = fabs((double)g.w);
+        if (pb_touches(B, (double)g.x, (double)g.y, (double)g.z, r, r)) {
+            if (cnt < PB_CAP) rec[1 + cnt] = (unsigned int)slot;
+            ++cnt;
+        }
+    };
+    for (int b = 0; b < bv.nbig; ++b) sphere(bv.big_geom[b], bv.big_slot[b]);
+    if (bv.m == 1) sphere(bv.geom[0], bv.slot[0]);
+    if (bv.m > 1) {
+        int stack[BVH_STACK];
+        int sp = 0, node = 0;
+        while (cnt <= PB_CAP) {
+            const float4 q0 = bv.nodes[4 * (size_t)node], q1 = bv.nodes[4 * (size_t)node + 1];
+            const float4 q2 = bv.nodes[4 * (size_t)node + 2], q3 = bv.nodes[4 * (size_t)node + 3];
+            const int child[2] = {__float_as_int(q3.x), __float_as_int(q3.y)};
+            const double lo[2][3] = {{q0.x, q0.y, q0.z}, {q1.z, q1.w, q2.x}}, hi[2][3] = {{q0.w, q1.x, q1.y}, {q2.y, q2.z, q2.w}};
+            const double rmin[2] = {fabs((double)q3.z), fabs((double)q3.w)};
+            int next = -1;
+            for (int c = 0; c < 2; ++c) {
+                if (child[c] < 0) { sphere(bv.geom[~child[c]], bv.slot[~child[c]]); continue; }
+                const double cx = 0.5 * (lo[c][0] + hi[c][0]), cy = 0.5 * (lo[c][1] + hi[c][1]), cz = 0.5 * (lo[c][2] + hi[c][2]);
+                const double ex = 0.5 * (hi[c][0] - lo[c][0]), ey = 0.5 * (hi[c][1] - lo[c][1]), ez = 0.5 * (hi[c][2] - lo[c][2]);
+                // the box corners were rounded to float when the tree was built: a relative 1e-6 covers that
+                const double rb = sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-6) + 1e-6 * (fabs(cx) + fabs(cy) + fabs(cz));
+                if (!pb_touches(B, cx, cy, cz, rb, rmin[c])) continue;
+                if (next < 0) next = child[c];
+                else if (sp < BVH_STACK) stack[sp++] = child[c];
+                else cnt = PB_CAP + 1;                                            // cannot happen for a 30-bit Morton tree; stay safe
+            }
+            if (next >= 0) { node = next; continue; }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    rec[0] = cnt <= PB_CAP ? (unsigned int)cnt : PB_OVERFLOW;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Persistent path tracer with binned camera rays (linear shared-memory scan for everything else).  Same jobs, same Philox
-// counters, same partial planes and therefore the same image, bit for bit, as trace_kernel<T, RT_ACCEL_LINEAR>.
+// Persistent path tracer with binned camera rays; the scattered segments go through the shared-memory scan
+// (ACCEL = RT_ACCEL_LINEAR) or the resumable LBVH traversal (RT_ACCEL_LBVH / ACCEL_LBVH_COMPACT, float).  Same jobs, same
+// Philox counters, same partial planes and therefore the same image, bit for bit, as trace_kernel<T, ACCEL>.
 //
-// A lane is in one of three phases: FRESH (starts the next sample of its job), HIT (a closest hit waits to be shaded),
-// RAY (a live ray waits for the scan).  One loop turn =
+// A lane is in one of four phases: FRESH (starts the next sample of its job), HIT (a closest hit waits to be shaded),
+// RAY (a live ray waits for the scan / for its traversal to start), FLY (LBVH: traversal in flight).  One loop turn =
 //   A  up to pb_rounds times: job fetch; FRESH lanes generate their camera ray and resolve it against the tile list --
 //      a miss adds the sky and leaves the lane FRESH for the next round, a hit makes it HIT;
 //   B  HIT lanes scatter (one Philox block, dimension depth+1) and become RAY, or end the path and become FRESH;
-//   C  one shared-memory scan for the RAY lanes; misses add the sky (FRESH), hits become HIT.
+//   C  one shared-memory scan for the RAY lanes (LBVH: RAY lanes start their traversal, then a bounded number of node
+//      visits for every lane in flight); misses add the sky (FRESH), hits become HIT.
 // so (almost) every lane that enters the scan carries a scattered ray.
-template <typename T>
+template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
+    constexpr bool LB = (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT);
+    constexpr bool RAYD = (ACCEL == ACCEL_LBVH_COMPACT);
+    static_assert(!LB || sizeof(T) == 4, "the LBVH is a float structure");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
-    stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
-    const SceneView<T> sc = view_of<T>(smem, A.scene);
-    unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
-    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene);
+    SceneView<T> sc;
+    unsigned short *cand = nullptr;
+    ScanGeom geo = scan_geom(0u, 0);
+    if constexpr (!LB) {
+        stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
+        sc = view_of<T>(smem, A.scene);
+        cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
+        geo = scan_geom(smem_u32(smem), A.scene);
+    } else {
+        sc = view_of<T>(A.scene.base, A.scene);
+    }
+    unsigned int n_nodes = 0, n_tests = 0;
+    BvhTrav tv;
+    BvhStack bvh_stack;
+    tv.node = -1;
 
     const int lane = threadIdx.x & 31;
     enum { NEED_JOB = 0, ACTIVE = 1, DEAD = 2 };
-    enum { FRESH = 0, HIT = 1, RAY = 2 };
+    enum { FRESH = 0, HIT = 1, RAY = 2, FLY = 3 };
     int state = NEED_JOB, phase = FRESH;
     PathState<T> ps;
     ps.o = A.cam.center;
@@ -129,7 +221,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
     uint32_t pixel = 0, tile = 0;
     unsigned long long job = 0;
-    unsigned int n_seg = 0, n_path = 0;
+    unsigned int n_seg = 0, n_path = 0, n_binned = 0;
 
     auto end_path = [&](T cr, T cg, T cb) {
         acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);
@@ -146,6 +238,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         T sr, sg, sb;
         sky<T>(ps.puy, sr, sg, sb);
         end_path(N::mul(ps.att.x, sr), N::mul(ps.att.y, sg), N::mul(ps.att.z, sb));
+    };
+    // a segment's closest hit is known: count it, then sky or pending hit
+    auto land = [&](const Hit<T> &h) {
+        ++n_seg;
+        if (h.id < 0) end_in_sky();
+        else { hit = h; phase = HIT; }
     };
 
     for (;;) {
@@ -188,30 +286,28 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
                 ph.block(0);
                 camera_ray(A, pi, pj, ph, ps);
                 depth = 0;
-                const uint4 *rec = reinterpret_cast<const uint4 *>(A.bins) + (size_t)tile * (PB_STRIDE / 8);
+                const uint4 *rec = reinterpret_cast<const uint4 *>(A.bins) + (size_t)tile * (PB_STRIDE / 4);
                 uint4 q = __ldg(rec);
-                const unsigned cnt = q.x & 0xffffu;
+                const unsigned cnt = q.x;
                 const T a = dot3(ps.d, ps.d);
                 const bool sane = a > T(1e-30) && a < T(1e30);        // false for NaN too: such rays take the scan's exact loop
                 if (cnt == PB_OVERFLOW || !sane) {
-                    phase = RAY;                                      // this camera ray goes through the shared-memory scan
+                    phase = RAY;                                      // this camera ray goes through the scan / the tree
                 } else {
                     Hit<T> h;
                     h.t = N::inf();
                     h.id = -1;
 #pragma unroll 1
                     for (unsigned e = 1; e <= cnt; ++e) {
-                        // the record is consumed 16 bits at a time: shift the 128-bit window, refill every 8 entries
-                        if ((e & 7u) == 0u) q = __ldg(rec + (e >> 3));
-                        else {
-                            q.x = __funnelshift_r(q.x, q.y, 16); q.y = __funnelshift_r(q.y, q.z, 16);
-                            q.z = __funnelshift_r(q.z, q.w, 16); q.w >>= 16;
-                        }
-                        resolve_slot<T>(geo.addr, (int)(q.x & 0xffffu), ps.o, ps.d, a, h);
+                        // the record is consumed one word at a time: rotate the 128-bit window, refill every 4 entries
+                        if ((e & 3u) == 0u) q = __ldg(rec + (e >> 2));
+                        else { q.x = q.y; q.y = q.z; q.z = q.w; }
+                        if constexpr (LB) bvh_test_sphere(__ldg(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
+                        else resolve_slot<T>(geo.addr, (int)q.x, ps.o, ps.d, a, h);
                     }
-                    ++n_seg;
-                    if (h.id < 0) end_in_sky();
-                    else { hit = h; phase = HIT; }
+                    n_tests += cnt;
+                    ++n_binned;
+                    land(h);
                 }
             }
         }
@@ -227,27 +323,49 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             else phase = RAY;
         }
 
-        // ---- C: closest hit over all slots for the scattered rays (all 32 lanes take part in the scan) ----
-        const bool scan = (state == ACTIVE && phase == RAY);
-        if (__any_sync(FULL, scan)) {
-            const Hit<T> h = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
-            if (scan) {
-                ++n_seg;
-                if (h.id < 0) end_in_sky();
-                else { hit = h; phase = HIT; }
+        // ---- C: closest hit of the scattered rays ----
+        if constexpr (LB) {
+            if (state == ACTIVE && phase == RAY) {
+                bvh_start<RAYD>(A.bvh, ps.o, ps.d, tv, n_tests);
+                phase = FLY;
+            }
+#pragma unroll 1
+            for (int step = 0; step < A.bvh_steps; ++step) {
+                const int flying_lanes = __popc(__ballot_sync(FULL, tv.node >= 0));
+                if (flying_lanes == 0 || (flying_lanes < A.bvh_min_active && step > 0)) break;
+                if (tv.node >= 0) bvh_step<RAYD>(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
+            }
+            if (state == ACTIVE && phase == FLY && tv.node < 0) land(tv.hit);
+        } else {
+            // all 32 lanes take part in the shared-memory scan; the ones without a live ray scan a stale one
+            const bool scan = (state == ACTIVE && phase == RAY);
+            if (__any_sync(FULL, scan)) {
+                const Hit<T> h = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+                if (scan) land(h);
             }
         }
     }
 
-    unsigned long long seg = n_seg, pth = n_path;
+    unsigned long long seg = n_seg, pth = n_path, bnd = n_binned;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         seg += __shfl_xor_sync(FULL, seg, off);
         pth += __shfl_xor_sync(FULL, pth, off);
+        bnd += __shfl_xor_sync(FULL, bnd, off);
     }
     if (lane == 0) {
         atomicAdd(A.queue + 1, seg);
         atomicAdd(A.queue + 2, pth);
+        atomicAdd(A.queue + 5, bnd);
+    }
+    if constexpr (LB) {
+        unsigned long long nod = n_nodes, tst = n_tests;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            nod += __shfl_xor_sync(FULL, nod, off);
+            tst += __shfl_xor_sync(FULL, tst, off);
+        }
+        if (lane == 0) { atomicAdd(A.queue + 3, nod); atomicAdd(A.queue + 4, tst); }
     }
 }
 

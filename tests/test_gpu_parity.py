@@ -385,6 +385,58 @@ def test_primary_bins_full_size_frame(renderer):
     assert np.array_equal(bits(on), bits(off))
 
 
+@pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 320, 192, 6, 25), (2, 200, 120, 8, 50), (3, 97, 61, 12, 50)])
+def test_primary_bins_lbvh_equal_the_full_traversal(renderer, scene_id, w, h, spp, depth):
+    """LBVH scenes: the lists come from bin_kernel_bvh (the bundle walks the tree).  Bins on == bins off == the linear scan
+    without bins, bit for bit, and the work counters agree."""
+    renderer.upload_scene(rt.scene(scene_id))
+    cam = rt.camera(w, h, spp, depth)
+    plain = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    seg = renderer.stats().segments
+    off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH, primary_bins=api.PBINS_OFF))
+    st_off = renderer.stats()
+    on = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH, primary_bins=api.PBINS_ON))
+    st_on = renderer.stats()
+    assert st_on.segments == st_off.segments == seg
+    assert st_on.binned_segments > 0 and st_off.binned_segments == 0
+    assert st_on.node_visits < st_off.node_visits
+    assert np.array_equal(bits(on), bits(off)) and np.array_equal(bits(on), bits(plain))
+
+
+def test_primary_bins_lbvh_100k_scene(renderer):
+    """BASELINE config 5's scene at config 2's frame size: near tiles are binned, tiles towards the horizon overflow and
+    keep the traversal; the frame is the one the plain traversal renders."""
+    renderer.upload_scene(rt.scene_scaled(158))
+    cam = rt.camera(1920, 1080, 1, 50)
+    off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH, primary_bins=api.PBINS_OFF))
+    seg = renderer.stats().segments
+    on = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH, primary_bins=api.PBINS_ON))
+    st = renderer.stats()
+    assert st.segments == seg
+    assert 0.2 * 1920 * 1080 < st.binned_segments <= 1920 * 1080
+    assert np.array_equal(bits(on), bits(off))
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_primary_bins_random_scenes(renderer, seed):
+    """Random sphere soups (sizes over two decades, some around the camera): bins on == bins off for both structures."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(40, 700))
+    s = np.zeros(n, dtype=api.SLOT_DTYPE)
+    s["c"] = rng.uniform(-12, 14, size=(n, 3)).astype(np.float32)
+    s["r"] = (10 ** rng.uniform(-1.5, 0.5, size=n)).astype(np.float32)
+    s["type"] = rng.integers(0, 3, size=n)
+    s["albedo"] = rng.uniform(0.2, 0.9, size=(n, 3)).astype(np.float32)
+    s["fuzz"] = np.where(s["type"] == 1, 0.2, 0).astype(np.float32)
+    s["ri"] = np.where(s["type"] == 2, 1.5, 0).astype(np.float32)
+    renderer.upload_scene(s)
+    cam = rt.camera(160, 96, 4, 8)
+    ref = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    for accel in (api.ACCEL_LINEAR, api.ACCEL_LBVH):
+        img = renderer.render(cam, api.make_opts(accel=accel, primary_bins=api.PBINS_ON))
+        assert np.array_equal(bits(img), bits(ref)), accel
+
+
 # ------------------------------------------------------------------ LBVH (RT_ACCEL_LBVH) ------
 @pytest.mark.parametrize("scene_id", [1, 2, 3])
 def test_lbvh_primary_equals_linear_scan(renderer, scene_id):
@@ -401,7 +453,7 @@ def test_lbvh_render_equals_linear_scan(renderer, scene_id, w, h, spp, depth):
     """Same hits => same paths => the same image, bit for bit."""
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    a = renderer.render(cam)
+    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     seg = renderer.stats().segments
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     st = renderer.stats()
@@ -418,7 +470,7 @@ def test_lbvh_mid_size_scene_equals_linear_scan(renderer):
     ids, t = renderer.primary_hits(cam)
     bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
-    a = renderer.render(cam)
+    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     assert np.array_equal(bits(a), bits(b))
 
@@ -461,7 +513,7 @@ def test_wavefront_equals_megakernel(renderer, scene_id, w, h, spp, depth):
     path counts."""
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    a = renderer.render(cam)
+    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     sa = renderer.stats()
     b = renderer.render(cam, api.make_opts(kernel=api.KERNEL_WAVEFRONT))
     sb = renderer.stats()
@@ -494,7 +546,7 @@ def test_bench_line_schema():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
         assert key in line, key
-    assert line["metric"] == "Mpath-samples/s" and line["value"] > 0 and line["gpu_launches"] == 4
+    assert line["metric"] == "Mpath-samples/s" and line["value"] > 0 and line["gpu_launches"] == 6       # 2 steps x (bin_kernel, trace_kernel_pb, finalize_kernel)
     assert line["e2e"]["h2d_bytes_per_step"] == 488 * 40 and line["e2e"]["d2h_bytes_per_step"] == 320 * 192 * 12
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert "workload" in line["config"]
@@ -523,7 +575,7 @@ def test_lbvh_random_scenes_equal_linear_scan(renderer, seed):
     ids, t = renderer.primary_hits(cam)
     bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
-    a = renderer.render(cam)
+    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     seg = renderer.stats().segments
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     assert renderer.stats().segments == seg

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in rt_b200.h but not exported"
     assert sorted(api.SYMBOLS) == names, "api.SYMBOLS and the header drifted apart"
-    assert rt.lib().rt_abi_version() == 1
+    assert rt.lib().rt_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
