@@ -179,12 +179,16 @@ __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, flo
     return ok ? tn : __int_as_float(0x7f800000);
 }
 
-// Same test with an inflation fixed per ray (op = o + delta, om = o - delta): 6 subtractions, 6 products, no square root.
-__device__ __forceinline__ float bvh_box_entry_ray(float lx, float ly, float lz, float hx, float hy, float hz, const Vec3<float> &op,
-                                                   const Vec3<float> &om, const Vec3<float> &inv, float limit) {
-    const float t0x = (lx - op.x) * inv.x, t1x = (hx - om.x) * inv.x;
-    const float t0y = (ly - op.y) * inv.y, t1y = (hy - om.y) * inv.y;
-    const float t0z = (lz - op.z) * inv.z, t1z = (hz - om.z) * inv.z;
+// Same test with an inflation fixed per ray and the origin folded into the products: opi = (o + delta) * inv,
+// omi = (o - delta) * inv, t = fma(bound, inv, -opi/omi) -- 6 FMAs per box, no square root (measured against 6 subtractions +
+// 6 products: -2 % on scene 1).  The rounded product moves a slab plane by at most one ulp of |o|, which the 8 ulp of
+// |o| + |box| inside the per-ray inflation (bvh_start<true>) already cover; an infinite inv (a zero direction component) can
+// turn a slab into NaN, which fminf/fmaxf drop -- the axis then does not constrain the box: conservative.
+__device__ __forceinline__ float bvh_box_entry_ray(float lx, float ly, float lz, float hx, float hy, float hz, const Vec3<float> &opi,
+                                                   const Vec3<float> &omi, const Vec3<float> &inv, float limit) {
+    const float t0x = fmaf(lx, inv.x, -opi.x), t1x = fmaf(hx, inv.x, -omi.x);
+    const float t0y = fmaf(ly, inv.y, -opi.y), t1y = fmaf(hy, inv.y, -omi.y);
+    const float t0z = fmaf(lz, inv.z, -opi.z), t1z = fmaf(hz, inv.z, -omi.z);
     const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
     const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
     const bool ok = tn <= fminf(fmaf(fabsf(tf), 1e-4f, tf) + 1e-30f, limit) && tf >= 0.0f;
@@ -204,7 +208,7 @@ struct BvhTrav {
     float a;
     Vec3<float> inv;      // 1/d
     Hit<float> hit;
-    Vec3<float> op, om;   // compact scenes (bvh_start<true>): o + delta, o - delta with one inflation for every box
+    Vec3<float> op, om;   // compact scenes (bvh_start<true>): (o + delta) * inv, (o - delta) * inv with one inflation for every box
 };
 
 template <bool RAYD = false>
@@ -241,6 +245,8 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
                             4.8e-7f * (omax + fmaxf(fmaxf(fx, fy), fz));
         tv.op.x = o.x + delta; tv.op.y = o.y + delta; tv.op.z = o.z + delta;
         tv.om.x = o.x - delta; tv.om.y = o.y - delta; tv.om.z = o.z - delta;
+        tv.op.x *= tv.inv.x; tv.op.y *= tv.inv.y; tv.op.z *= tv.inv.z;
+        tv.om.x *= tv.inv.x; tv.om.y *= tv.inv.y; tv.om.z *= tv.inv.z;
     }
 }
 
@@ -263,6 +269,8 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
         tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, tv.inv, limit);
         tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, tv.inv, limit);
     }
+    // leaf tests run inline: parking them per lane to run the tests of many lanes together was measured 4 % SLOWER (the
+    // closest hit shrinks later, and the flush adds two ballots per step)
     if (tl < inf && left < 0) {
         bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, tv.a, tv.hit);
         ++n_tests;

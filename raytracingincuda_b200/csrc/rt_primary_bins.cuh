@@ -33,7 +33,10 @@
 
 namespace rt {
 
-constexpr int PB_SHIFT = 4;                 // tiles of 16 x 16 pixels
+#ifndef RT_PB_SHIFT
+#define RT_PB_SHIFT 4
+#endif
+constexpr int PB_SHIFT = RT_PB_SHIFT;       // tiles of 16 x 16 pixels
 constexpr int PB_STRIDE = 32;               // uint32 per tile record: [0] = count or PB_OVERFLOW, [1..31] = slots
 constexpr int PB_CAP = PB_STRIDE - 1;
 constexpr unsigned PB_OVERFLOW = 0xffffffffu;
@@ -181,8 +184,12 @@ __global__ void __launch_bounds__(128) bin_kernel_bvh(const __grid_constant__ De
 //   C  one shared-memory scan for the RAY lanes (LBVH: RAY lanes start their traversal, then a bounded number of node
 //      visits for every lane in flight); misses add the sky (FRESH), hits become HIT.
 // so (almost) every lane that enters the scan carries a scattered ray.
+#ifndef RT_TRACE_MIN_BLOCKS_LBVH
+#define RT_TRACE_MIN_BLOCKS_LBVH 4     // the traversal is latency bound: 4 CTAs of 64 registers beat 3 of 80 (99 860 slots: -7 %)
+#endif
 template <typename T, int ACCEL>
-__global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
+__global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? (ACCEL == RT_ACCEL_LINEAR ? RT_TRACE_MIN_BLOCKS : RT_TRACE_MIN_BLOCKS_LBVH) : 2)
+trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
     constexpr bool LB = (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT);
     constexpr bool RAYD = (ACCEL == ACCEL_LBVH_COMPACT);

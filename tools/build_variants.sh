@@ -12,7 +12,7 @@ for spec in "$@"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -I$ROOT/include $flags \
       -Xptxas -v -c $ROOT/raytracingincuda_b200/csrc/rt_kernels.cu -o $OUT/k_$name.o 2> $OUT/ptxas_$name.log
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/librt_b200_$name.so $OUT/k_$name.o $OUT/rt_host.o -cudart shared
-  echo "$name: $(grep -A2 'trace_kernelIfLi0' $OUT/ptxas_$name.log | grep -E 'Used' | head -1)"
+  echo "$name: $(grep -A2 'trace_kernel_pbIfLi[03]' $OUT/ptxas_$name.log | grep -E 'Used' | head -1)"
   ) &
 done
 wait
