@@ -182,8 +182,8 @@ __device__ __forceinline__ float bvh_box_entry(float lx, float ly, float lz, flo
 // Same test with an inflation fixed per ray and the origin folded into the products: opi = (o + delta) * inv,
 // omi = (o - delta) * inv, t = fma(bound, inv, -opi/omi) -- 6 FMAs per box, no square root (measured against 6 subtractions +
 // 6 products: -2 % on scene 1).  The rounded product moves a slab plane by at most one ulp of |o|, which the 8 ulp of
-// |o| + |box| inside the per-ray inflation (bvh_start<true>) already cover; an infinite inv (a zero direction component) can
-// turn a slab into NaN, which fminf/fmaxf drop -- the axis then does not constrain the box: conservative.
+// |o| + |box| inside the per-ray inflation (bvh_start<true>) already cover.  bvh_start<true> keeps |inv| <= 1e30 so that no
+// product is infinite (see there).
 __device__ __forceinline__ float bvh_box_entry_ray(float lx, float ly, float lz, float hx, float hy, float hz, const Vec3<float> &opi,
                                                    const Vec3<float> &omi, const Vec3<float> &inv, float limit) {
     const float t0x = fmaf(lx, inv.x, -opi.x), t1x = fmaf(hx, inv.x, -omi.x);
@@ -245,6 +245,13 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
                             4.8e-7f * (omax + fmaxf(fmaxf(fx, fy), fz));
         tv.op.x = o.x + delta; tv.op.y = o.y + delta; tv.op.z = o.z + delta;
         tv.om.x = o.x - delta; tv.om.y = o.y - delta; tv.om.z = o.z - delta;
+        // The products below must stay finite: with an infinite 1/d (a zero direction component) fma(bound, inf, -inf) is NaN
+        // for one plane of a slab and -inf for the other, and fminf/fmaxf would then REJECT a box the ray starts inside of
+        // (seen twice in 96 million segments).  |1/d| <= 1e30 treats such a component as 1e-30: over any t that can reach the
+        // scene the ray does not move along that axis either way, so inside/outside of the inflated slab decides, as it should.
+        tv.inv.x = fminf(fmaxf(tv.inv.x, -1e30f), 1e30f);
+        tv.inv.y = fminf(fmaxf(tv.inv.y, -1e30f), 1e30f);
+        tv.inv.z = fminf(fmaxf(tv.inv.z, -1e30f), 1e30f);
         tv.op.x *= tv.inv.x; tv.op.y *= tv.inv.y; tv.op.z *= tv.inv.z;
         tv.om.x *= tv.inv.x; tv.om.y *= tv.inv.y; tv.om.z *= tv.inv.z;
     }
