@@ -434,9 +434,9 @@ def run_b200_arm(args):
                          "kernel_ms": round(step_trace_ms, 3), "traffic": None},
         }
         # DRAM bytes per trace_kernel launch from the committed ncu pass over this same command
-        # (profiles/r01_bench_kernel_traffic.json); None for workloads that were not captured
+        # (profiles/r01e_bench_kernel_traffic.json); None for workloads that were not captured
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_bench_kernel_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01e_bench_kernel_traffic.json")) as f:
                 cap = json.load(f).get(args.workload, {})
             k = next(v for name, v in cap.items() if "trace_kernel" in name)
             if world == 1 and not lbvh:

@@ -274,8 +274,8 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                         pj = global_row(A, lr);
                         pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
                         tile = (uint32_t)(pj >> PB_SHIFT) * (uint32_t)A.tiles_x + (uint32_t)(pi >> PB_SHIFT);
-                        sample = (int)((long long)c * A.spp / A.chunks);
-                        sample_end = (int)((long long)(c + 1) * A.spp / A.chunks);
+                        sample = first_sample(A, c);
+                        sample_end = first_sample(A, c + 1);
                         acc_r = acc_g = acc_b = T(0);
                         state = ACTIVE;
                         phase = FRESH;
