@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
                 if (job < A.total_jobs) {
                     // exact divisions by multiply-high (job * pix_local and lp * width stay far below 2^64)
                     const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;            // magic 0: divisor 1
-                    const unsigned long long lp = job - cl * A.pix_local;
+                    // pixels of a chunk are handed out last to first (bottom rows first, see trace_kernel_pb); from here on
+                    // `job` is the index of the job's sum in the partial planes
+                    const unsigned long long lp = A.pix_local - 1ull - (job - cl * A.pix_local);
+                    job = cl * A.pix_local + lp;
                     const int c = A.c_begin + (int)cl;
                     const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
                     pi = (int)(lp - (unsigned long long)lr * A.width);
