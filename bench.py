@@ -370,7 +370,13 @@ def run_b200_arm(args):
 
     t = torch.tensor([ms, e2e_s * 1e3, step_trace_ms], dtype=torch.float64, device=device)
     seg_t = torch.tensor([segments, tests[0], nodes[0], binned[0]], dtype=torch.int64, device=device)
+    per_rank_ms = [step_trace_ms]
     if world > 1:
+        # every rank's own path-tracing time per step: the step ends with the slowest rank
+        mine = torch.tensor([step_trace_ms], dtype=torch.float64, device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_ms = [round(float(x.item()), 3) for x in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(seg_t, op=dist.ReduceOp.SUM)
     ms, e2e_ms, step_trace_ms = [float(x) for x in t.tolist()]
@@ -446,6 +452,8 @@ def run_b200_arm(args):
         except Exception:
             pass
         st = r.stats()
+        if world > 1:
+            line["per_rank_kernel_ms"] = per_rank_ms
         line["kernel"] = {"grid": st.grid, "block": st.block, "regs": st.regs, "smem_bytes": st.smem_bytes,
                           "segments_per_path": round(segments / paths, 4),
                           "binned_segments_per_path": round(binned_segments / paths, 4)}

@@ -189,6 +189,12 @@ int orc_num_chunks(int width, int height, int spp) {
     int64_t npix = (int64_t)width * height;
     int64_t want = (((int64_t)1 << 22) + npix - 1) / npix;
     int64_t c = 8 * ((want + 7) / 8);
+    /* at most 32 samples per job (multiples of 8 chunks), partial planes below 8 GiB */
+    int64_t by_spp = 8 * (((int64_t)spp + 255) / 256);
+    int64_t by_mem = 8 * ((((int64_t)1 << 33) / (npix * 16)) / 8);
+    if (by_mem < 8) by_mem = 8;
+    if (by_spp > by_mem) by_spp = by_mem;
+    if (by_spp > c) c = by_spp;
     int64_t cap = 8 * (int64_t)(spp / 8);
     if (c > cap) c = cap;
     if (c > 1024) c = 1024;

@@ -12,6 +12,7 @@ import pytest
 
 import raytracingincuda_b200 as rt
 from raytracingincuda_b200 import api
+import oracle_lib as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "raytracingincuda_b200", "bin", "b200-raytrace")
@@ -94,7 +95,10 @@ def test_partitions():
         assert b[0][0] == 0 and b[-1][1] == c and all(x[1] == y[0] for x, y in zip(b, b[1:]))
     with pytest.raises(rt.RtError):
         rt.partition_rows(10, 8, 2, 2)
-    assert rt.num_chunks(3840, 2160, 1000) == 8 and rt.num_chunks(320, 192, 4096) == 72
+    assert rt.num_chunks(3840, 2160, 1000) == 32 and rt.num_chunks(320, 192, 4096) == 128
+    for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 10), (320, 192, 4096), (320, 192, 5), (8, 8, 100000),
+                      (7680, 4320, 100000), (640, 360, 17), (3840, 2160, 256), (97, 61, 12)]:
+        assert rt.num_chunks(w, h, spp) == O.num_chunks(w, h, spp), (w, h, spp)
 
 
 def test_ppm_writer_matches_reference_format(tmp_path, golden_dir):

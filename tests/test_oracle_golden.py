@@ -135,10 +135,12 @@ def test_hit_world_edge_cases():
 
 
 def test_chunk_layout():
-    assert O.num_chunks(3840, 2160, 1000) == 8
+    assert O.num_chunks(3840, 2160, 1000) == 32              # at most 32 samples per job
     assert O.num_chunks(1920, 1080, 100) == 8
     assert O.num_chunks(320, 192, 10) == 8
-    assert O.num_chunks(320, 192, 4096) == 72
+    assert O.num_chunks(320, 192, 4096) == 128
+    assert O.num_chunks(3840, 2160, 256) == 8
+    assert O.num_chunks(7680, 4320, 100000) == 16            # partial planes stay below 8 GiB
     assert O.num_chunks(320, 192, 5) == 5
     assert O.num_chunks(8, 8, 100000) == 1024
     for spp in (9, 17, 100, 1000):
