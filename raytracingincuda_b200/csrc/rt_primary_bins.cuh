@@ -27,7 +27,8 @@
 // slot can only matter if some axis point satisfies |X0(s) - c| <= R0 + kappa * s|a|, R0 = r_eff + rho, kappa = (hT + rho)/|a|,
 // a = Q0 - L0.  Minimising the left side minus the right side over ALL real s (a superset of s > 0) gives the closed form
 //   perp * sqrt(1 - kappa^2) - kappa * along <= R0,        along = (c - L0).a/|a|,  perp = distance of c from the axis,
-// which bin_kernel evaluates in double with absolute and relative margins that dwarf the float rounding of camera_ray
+// A second necessary condition removes the 2 rho this linear bound carries around the focus plane (pb_touches).  Both are
+// evaluated in double with absolute and relative margins that dwarf the float rounding of camera_ray
 // (|px|, |py| round monotonically, so they stay inside the tile; L and Q move by a few 1e-7 relative).
 #pragma once
 
@@ -46,6 +47,7 @@ constexpr double PB_NOISE = 64.0 * 5.9604644775390625e-08;      // 64 * 2^-24, s
 struct PbBundle {
     double L0[3], ah[3];        // lens centre, unit axis
     double kappa, cosk, rho, margin;
+    double la, hT;              // |a|, half extent of the tile on the focus plane
     bool ok;                    // false: degenerate camera or a very wide tile -> PB_OVERFLOW
 };
 
@@ -82,6 +84,8 @@ __device__ __forceinline__ PbBundle pb_bundle(const DevCamera<T> &cam, int tile,
     B.kappa = (hT + B.rho + B.margin) / la * (1.0 + 1e-6);
     B.ok = (la > 0.0) && (B.kappa < 0.5) && (B.rho < 1e300) && (B.margin < 1e300);   // false for NaN/inf cameras too
     B.cosk = B.ok ? sqrt(1.0 - B.kappa * B.kappa) : 0.0;
+    B.la = la;
+    B.hT = hT;
     const double inv_la = B.ok ? 1.0 / la : 0.0;
     for (int q = 0; q < 3; ++q) B.ah[q] = a[q] * inv_la;
     return B;
@@ -99,7 +103,16 @@ __device__ __forceinline__ bool pb_touches(const PbBundle &B, double cx, double 
     const double reach = radius + (sqrt(rmin * rmin + PB_NOISE * D * D) - rmin);
     const double R0 = reach + B.rho + B.margin;
     const double lhs = perp * B.cosk, rhs = (R0 + B.kappa * along) * (1.0 + 1e-9) + B.margin;
-    return !(lhs > rhs);                                                          // NaN geometry counts as a candidate
+    if (lhs > rhs) return false;
+    // Second necessary condition, tight where the first is loose (around the focus plane the lens term of the bundle radius
+    // vanishes, the linear bound above carries 2 rho there).  The first condition confines the axis points that can matter to
+    // arc lengths u in [u_lo, u_hi]; the exact bundle radius w(u) = |1 - u/|a|| rho + (u/|a|) hT is convex, so it is at most
+    // max(w(u_lo), w(u_hi)) there, and the ball must reach the axis within that: perp <= reach + w_max.
+    const double u_lo = fmax((along - R0) / (1.0 + B.kappa), 0.0), u_hi = fmax((along + R0) / (1.0 - B.kappa), 0.0);
+    const double rl = (B.rho + B.margin) * (1.0 + 1e-6), hl = (B.hT + B.margin) * (1.0 + 1e-6);
+    const double s_lo = u_lo / B.la, s_hi = u_hi / B.la;
+    const double w_max = fmax(fabs(1.0 - s_lo) * rl + s_lo * hl, fabs(1.0 - s_hi) * rl + s_hi * hl);
+    return !(perp > (reach + w_max) * (1.0 + 1e-9) + B.margin);                   // NaN geometry counts as a candidate
 }
 
 // one thread per tile, every slot of the scene (linear-scan scenes: a few hundred to a few thousand slots)
