@@ -1182,6 +1182,7 @@ int check_opts(const rt_opts &o) {
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
     if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO) return RT_EINVAL;
     if (o.kernel != RT_KERNEL_MEGA && o.kernel != RT_KERNEL_WAVEFRONT) return RT_EINVAL;
+    if (o.primary_bins < RT_PBINS_AUTO || o.primary_bins > RT_PBINS_ON) return RT_EINVAL;
     if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel == RT_ACCEL_LBVH) return RT_EINVAL;
     return RT_OK;
 }

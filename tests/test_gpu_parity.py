@@ -717,3 +717,6 @@ def test_invalid_inputs_fail_loudly(renderer):
         renderer.render(cam, out=np.zeros((8, 8, 3), dtype=np.float32))
     one = renderer.render(rt.camera(1, 1, 1, 1))           # the smallest frame there is
     assert one.shape == (1, 1, 3) and np.isfinite(one).all()
+    with pytest.raises(rt.RtError) as e:
+        renderer.render(rt.camera(8, 8, 1, 1), api.make_opts(primary_bins=7))
+    assert e.value.code == -1                              # RT_EINVAL
