@@ -6,6 +6,9 @@
 //                    warp-aggregated atomic (ballot + popc), so all 32 lanes stay inside the
 //                    sphere scan.  Replaces init_rng + render (GF rtweekend.h:43-50,
 //                    GF camera.h:78-172).
+//   trace_kernel_pb  (rt_primary_bins.cuh, the default) the same persistent tracer with the camera rays resolved against
+//                    per-tile candidate lists that bin_kernel / bin_kernel_bvh build on the device before the frame;
+//                    scattered rays go through the shared-memory scan or the LBVH.  Same image, bit for bit.
 //   finalize_kernel  sums the chunk partials in chunk order, scales, gamma-encodes and writes
 //                    the frame with 16-byte vector stores (GF camera.h:167-171, color.h:10-13).
 //   primary_kernel   deterministic primary-ray (slot id, t) pass through the same closest-hit

@@ -259,8 +259,8 @@ int main(int argc, char **argv) {
         }
     }
 
-    unsigned long long segments = 0, paths = 0;
-    for (auto &d : dev) { segments += d.stats.segments; paths += d.stats.paths; }
+    unsigned long long segments = 0, paths = 0, binned = 0;
+    for (auto &d : dev) { segments += d.stats.segments; paths += d.stats.paths; binned += d.stats.binned_segments; }
     const rt_stats st0 = dev[0].stats;
     for (auto &d : dev) rt_destroy(d.ctx);
     const auto e2e_stop = std::chrono::steady_clock::now();
@@ -272,9 +272,10 @@ int main(int argc, char **argv) {
         std::fprintf(stderr,
                      "{\"mpath_samples_per_s\": %.3f, \"paths\": %llu, \"segments\": %llu, \"slots\": %d, "
                      "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d, "
-                     "\"accel\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu}\n",
+                     "\"accel\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu, \"binned_segments\": %llu}\n",
                      mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks,
-                     st0.node_visits ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests);
+                     st0.node_visits ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests,
+                     binned);
     }
     return 0;
 }

@@ -596,6 +596,9 @@ def test_cli_end_to_end(tmp_path):
     assert p.returncode == 0, p.stderr
     assert re.fullmatch(r" {0,14}\d+\.\d{8}, {0,14}\d+\.\d{8}\n", p.stdout), repr(p.stdout)
     assert len(p.stdout) == 15 + 1 + 15 + 1
+    import json
+    stats = json.loads(p.stderr.strip().splitlines()[-1])                 # --stats: one JSON object on stderr
+    assert stats["paths"] == 64 * 40 * 4 and stats["binned_segments"] == stats["paths"] and stats["segments"] > stats["paths"]
     name = "b200_float_scene2_64x40_4samples_5bounces_16threadsPerBlockRow.ppm"
     assert os.listdir(tmp_path) == [name]
     ref, _ = O.render(O.scene(2), O.camera(64, 40, 4, 5))
