@@ -940,7 +940,7 @@ int build_lbvh(rt_ctx *ctx) {
     ctx->bvh.big_geom = big_geom; ctx->bvh.big_slot = big_slot;
     ctx->bvh.m = m; ctx->bvh.nbig = nbig;
     // bounds and smallest radius of the tree's spheres.  The scene counts as compact when the single per-ray box inflation
-    // (bvh_start<true>) stays below 5 % of the smallest radius for every origin within one bounds-diagonal of the tree.
+    // (bvh_start<true>) stays below 10 % of the smallest radius for every origin within one bounds-diagonal of the tree.
     float rmin_all = INFINITY, diag2 = 0.f;
     for (int q = 0; q < 3; ++q) { ctx->bvh.blo[q] = INFINITY; ctx->bvh.bhi[q] = -INFINITY; }
     for (int i : small_idx) {
@@ -955,7 +955,7 @@ int build_lbvh(rt_ctx *ctx) {
     if (m > 1 && ctx->bvh.rmin_all > 0.f && std::isfinite(diag2)) {
         const float reach = 2.f * std::sqrt(diag2);
         const float delta = std::sqrt(BVH_KEPS * reach * reach + rmin_all * rmin_all) - rmin_all;
-        ctx->bvh.compact = (delta <= 0.05f * rmin_all && !getenv("RT_BVH_NO_COMPACT")) ? 1 : 0;
+        ctx->bvh.compact = (delta <= 0.10f * rmin_all && !getenv("RT_BVH_NO_COMPACT")) ? 1 : 0;
     }
     ctx->bvh_ready = true;
     return RT_OK;

@@ -12,10 +12,10 @@
 // (the reference's shrinking-tmax test accepts S iff v(S) < closest).  The traversal evaluates
 // v(S) with the reference's exact arithmetic (disc_of / roots) at the leaves, so it only has to
 // be CONSERVATIVE about which leaves it visits.  In float the reference's discriminant carries an
-// error of up to ~8 ulp of a*|oc|^2, i.e. a sphere behaves as if its radius^2 were
-// r^2 + 16*eps*D^2 for a ray whose origin is D away -- far-away rays see "noisy" hits around small
+// error of up to 2^-24 * (21 |oc|^2 + 7 r^2) * a, i.e. a sphere behaves as if its radius^2 were at most
+// r^2 + 32*2^-24*D^2 for a ray whose origin is D away -- far-away rays see "noisy" hits around small
 // spheres.  Child boxes are therefore inflated per ray by
-//   delta = sqrt(rmin^2 + KEPS*D^2) - rmin
+//   delta = sqrt(rmin^2 + KEPS*D^2) - rmin        (KEPS = 32 * 2^-24)
 // where D bounds the distance from the ray origin to the box and rmin is the smallest radius
 // below the child; the slab comparison itself carries a 1e-5 relative slack for its own rounding
 // and nodes are culled against best_t with a 1e-4 relative slack.
@@ -39,7 +39,9 @@ struct BvhView {
     int compact;
 };
 
-constexpr float BVH_KEPS = 16.0f * 5.9604645e-8f;   // 16 * 2^-24
+// 32 * 2^-24: the worst-case bound of the reference's discriminant error is 2^-24 * (21 |oc|^2 + 7 r^2) (DESIGN.md section 6,
+// "Error bound" (i)); D bounds |oc| from above and, for a sphere inside the box, r as well
+constexpr float BVH_KEPS = 32.0f * 5.9604645e-8f;
 constexpr int BVH_STACK = 64;
 
 // ------------------------------------------------------------------------------ build ------
