@@ -149,6 +149,18 @@ def test_chunk_layout():
         assert edges[0] == 0 and edges[-1] == spp and all(b > a for a, b in zip(edges, edges[1:]))
 
 
+def test_chunk_edges_without_the_wide_division():
+    """The kernels compute a chunk's first sample as c*(spp // C) + c*(spp % C) // C in 32-bit arithmetic (rt_kernels.cu
+    first_sample); it must equal floor(c * spp / C), the oracle's edge, and c * (spp % C) must stay below 2^31."""
+    for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 4096), (8, 8, 100000), (640, 360, 17), (97, 61, 1023),
+                      (7680, 4320, 100000), (64, 40, 2147483647)]:
+        C = O.num_chunks(w, h, spp)
+        q, r = divmod(spp, C)
+        assert C <= 1024 and C * r < 2 ** 31
+        for c in list(range(0, C + 1, max(1, C // 37))) + [C]:
+            assert c * q + (c * r) // C == (c * spp) // C
+
+
 def test_render_sample_decomposition_and_rows():
     """render == per-pixel chunked sum of orc_sample, and row bands tile the frame."""
     s = O.scene(3)
