@@ -248,6 +248,42 @@ __device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) 
     return (tile * A.world + A.rank) * A.tile_rows + within;
 }
 
+// Job = (pixel, chunk), numbered chunk-major.  decode_job turns a queue index into the place of the job's sum in the partial
+// planes, the pixel and the sample range.  The pixels of a chunk are handed out last to first, i.e. bottom rows first: the
+// kernel ends when the last job ends, and a sky pixel's job is a fraction of an average one, so the jobs that run while the
+// machine drains should be the top rows (sky in the reference's scenes).
+struct JobInfo {
+    unsigned long long store;          // index of the job's float4 in the partial planes
+    int pi, pj, sample, sample_end;
+    uint32_t pixel;
+};
+template <typename T>
+__device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned long long job) {
+    JobInfo J;
+    // exact divisions by multiply-high (job * pix_local and lp * width stay far below 2^64)
+    const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;            // magic 0: divisor 1
+    const unsigned long long lp = A.pix_local - 1ull - (job - cl * A.pix_local);
+    J.store = cl * A.pix_local + lp;
+    const int c = A.c_begin + (int)cl;
+    const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
+    J.pi = (int)(lp - (unsigned long long)lr * A.width);
+    J.pj = global_row(A, lr);
+    J.pixel = (uint32_t)J.pj * (uint32_t)A.width + (uint32_t)J.pi;
+    J.sample = first_sample(A, c);
+    J.sample_end = first_sample(A, c + 1);
+    return J;
+}
+
+// One atomic per warp for all lanes that ran out of work (`want` = ballot of those lanes): this lane's queue index.
+template <typename T>
+__device__ __forceinline__ unsigned long long claim_job(const TraceArgs<T> &A, int lane, unsigned want) {
+    const int leader = __ffs(want) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
+    base = __shfl_sync(FULL, base, leader);
+    return base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+}
+
 template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLOCKS : 2) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
@@ -310,26 +346,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         // ---- job fetch: one atomic per warp for all lanes that ran out of work ----
         const unsigned want = __ballot_sync(FULL, state == NEED_JOB);
         if (want) {
-            const int leader = __ffs(want) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
-            base = __shfl_sync(FULL, base, leader);
+            const unsigned long long claimed = claim_job(A, lane, want);
             if (state == NEED_JOB) {
-                job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
-                if (job < A.total_jobs) {
-                    // exact divisions by multiply-high (job * pix_local and lp * width stay far below 2^64)
-                    const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;            // magic 0: divisor 1
-                    // pixels of a chunk are handed out last to first (bottom rows first, see trace_kernel_pb); from here on
-                    // `job` is the index of the job's sum in the partial planes
-                    const unsigned long long lp = A.pix_local - 1ull - (job - cl * A.pix_local);
-                    job = cl * A.pix_local + lp;
-                    const int c = A.c_begin + (int)cl;
-                    const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
-                    pi = (int)(lp - (unsigned long long)lr * A.width);
-                    pj = global_row(A, lr);
-                    pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
-                    sample = first_sample(A, c);
-                    sample_end = first_sample(A, c + 1);
+                if (claimed < A.total_jobs) {
+                    const JobInfo J = decode_job(A, claimed);
+                    job = J.store;
+                    pi = J.pi; pj = J.pj; pixel = J.pixel;
+                    sample = J.sample; sample_end = J.sample_end;
                     acc_r = acc_g = acc_b = T(0);
                     state = ACTIVE;
                     fresh = true;

@@ -272,29 +272,14 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
         for (int round = 0; round < A.pb_rounds; ++round) {
             const unsigned want = __ballot_sync(FULL, state == NEED_JOB);
             if (want) {
-                const int leader = __ffs(want) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
-                base = __shfl_sync(FULL, base, leader);
+                const unsigned long long claimed = claim_job(A, lane, want);
                 if (state == NEED_JOB) {
-                    job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
-                    if (job < A.total_jobs) {
-                        const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;
-                        // The pixels of a chunk are handed out last to first, i.e. bottom rows first: the kernel ends when the
-                        // last job ends, and a job is 6 ms of wall clock on average (125 samples at config 4) but a fraction of
-                        // that for a sky pixel, so the jobs that run while the machine drains should be the top rows (sky in the
-                        // reference's scenes).  Matters with 8 GPUs, where the drain is 4-5 % of a 430 ms step.
-                        // From here on `job` is the index of the job's sum in the partial planes.
-                        const unsigned long long lp = A.pix_local - 1ull - (job - cl * A.pix_local);
-                        job = cl * A.pix_local + lp;
-                        const int c = A.c_begin + (int)cl;
-                        const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
-                        pi = (int)(lp - (unsigned long long)lr * A.width);
-                        pj = global_row(A, lr);
-                        pixel = (uint32_t)pj * (uint32_t)A.width + (uint32_t)pi;
+                    if (claimed < A.total_jobs) {
+                        const JobInfo J = decode_job(A, claimed);
+                        job = J.store;                                   // from here on: where the job's sum is stored
+                        pi = J.pi; pj = J.pj; pixel = J.pixel;
+                        sample = J.sample; sample_end = J.sample_end;
                         tile = (uint32_t)(pj >> PB_SHIFT) * (uint32_t)A.tiles_x + (uint32_t)(pi >> PB_SHIFT);
-                        sample = first_sample(A, c);
-                        sample_end = first_sample(A, c + 1);
                         acc_r = acc_g = acc_b = T(0);
                         state = ACTIVE;
                         phase = FRESH;
