@@ -65,6 +65,24 @@ def tile_list(B, slots):
     return set(np.nonzero(first & second)[0].tolist())
 
 
+def touches(B, c, radius, rmin):
+    """pb_touches for one ball (a sphere: radius = rmin = r; the bounding ball of a BVH box: half diagonal, smallest radius inside)."""
+    b = np.asarray(c, dtype=np.float64) - B["L0"]
+    bb = b @ b
+    along = b @ B["ah"]
+    perp = np.sqrt(max(bb - along * along, 0.0))
+    D = np.sqrt(bb) + radius + B["rho"] + B["margin"]
+    reach = radius + (np.sqrt(rmin * rmin + PB_NOISE * D * D) - rmin)
+    R0 = reach + B["rho"] + B["margin"]
+    if perp * B["cosk"] > (R0 + B["kappa"] * along) * (1 + 1e-9) + B["margin"]:
+        return False
+    u_lo, u_hi = max((along - R0) / (1 + B["kappa"]), 0.0), max((along + R0) / (1 - B["kappa"]), 0.0)
+    rl, hl = (B["rho"] + B["margin"]) * (1 + 1e-6), (B["hT"] + B["margin"]) * (1 + 1e-6)
+    s_lo, s_hi = u_lo / B["la"], u_hi / B["la"]
+    w_max = max(abs(1 - s_lo) * rl + s_lo * hl, abs(1 - s_hi) * rl + s_hi * hl)
+    return not perp > (reach + w_max) * (1 + 1e-9) + B["margin"]
+
+
 def tile_rays(cam, B, rng, n_random):
     """Camera rays of the tile the way camera_ray builds them (float fma chains), at the extremes of the two draws and at
     random ones.  Yields (o, d) as float32 triples."""
@@ -162,3 +180,32 @@ def test_list_is_tight_around_a_single_sphere():
             listed[ty, tx] = 0 in tile_list(bundle(cam, tx, ty), s)
     assert listed[ids >= 0].all()                    # conservative
     assert listed.sum() <= 2.5 * max(1, (ids >= 0).sum()) + 40      # and not much more than the silhouette plus a rim of tiles
+
+
+@pytest.mark.parametrize("frame", [(320, 192), (3840, 2160)])
+def test_a_box_is_visited_when_a_sphere_inside_it_is_hit(frame):
+    """bin_kernel_bvh prunes a subtree when the bounding ball of its box (float corners, as the LBVH build rounds them) fails
+    pb_touches with the subtree's smallest radius.  Whenever a camera ray of the tile hits a sphere, every box that contains
+    that sphere must pass -- checked on boxes around the k nearest neighbours of the hit sphere, k = 1 .. 64."""
+    slots = O.scene(1)
+    cam = O.camera(*frame)
+    rng = np.random.default_rng(frame[0])
+    c, r = slots["c"].astype(np.float32), np.abs(slots["r"].astype(np.float32))
+    small = np.nonzero((r > 0.05) & (r < 5))[0]                          # the tree's spheres (ground and zero-radius slot stay outside)
+    tiles_x, tiles_y = (cam.width + 15) >> 4, (cam.height + 15) >> 4
+    checked = 0
+    for _ in range(60):
+        B = bundle(cam, int(rng.integers(0, tiles_x)), int(rng.integers(0, tiles_y)))
+        hit = {hit_slot(slots, o, d) for o, d in tile_rays(cam, B, rng, 8)}
+        for s in hit & set(small.tolist()):
+            order = small[np.argsort(((c[small] - c[s]) ** 2).sum(axis=1))]
+            for k in (1, 2, 5, 16, 64):
+                grp = order[:k]
+                lo = (c[grp] - r[grp, None]).min(axis=0)                    # float32, like bvh_leaves_kernel / bvh_refit_kernel
+                hi = (c[grp] + r[grp, None]).max(axis=0)
+                ctr = 0.5 * (lo.astype(np.float64) + hi.astype(np.float64))
+                ext = 0.5 * (hi.astype(np.float64) - lo.astype(np.float64))
+                rb = np.sqrt(ext @ ext) * (1 + 1e-6) + 1e-6 * np.abs(ctr).sum()
+                assert touches(B, ctr, rb, float(r[grp].min())), (frame, s, k)
+                checked += 1
+    assert checked > 200
