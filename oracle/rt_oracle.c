@@ -208,6 +208,23 @@ int orc_quantise(float x) {
     return (int)(256 * x);                                              /* main.cu:373-375 */
 }
 
+/* ------------------------------------------------------------------ segment log ------------ */
+/* Analysis aid (tools/analyse_accel.py): while a buffer is installed, every hit_world call of the path tracer appends
+ * {o.xyz, d.xyz, t (inf on a miss), slot id (-1), depth} as 9 floats.  Not used by any test of the render path. */
+static float *g_seg_log = 0;
+static long g_seg_cap = 0, g_seg_n = 0;
+void orc_log_segments(float *buf, long capacity) { g_seg_log = buf; g_seg_cap = buf ? capacity : 0; g_seg_n = 0; }
+long orc_logged_segments(void) { return g_seg_n; }
+static void log_segment(double ox, double oy, double oz, double dx, double dy, double dz, double t, int id, int depth) {
+    if (!g_seg_log) return;
+    if (g_seg_n < g_seg_cap) {
+        float *r = g_seg_log + 9 * g_seg_n;
+        r[0] = (float)ox; r[1] = (float)oy; r[2] = (float)oz; r[3] = (float)dx; r[4] = (float)dy; r[5] = (float)dz;
+        r[6] = id < 0 ? INFINITY : (float)t; r[7] = (float)id; r[8] = (float)depth;
+    }
+    ++g_seg_n;
+}
+
 /* ------------------------------------------------------------------ float instantiation --- */
 #define REAL float
 #define SFX(n) n##_f

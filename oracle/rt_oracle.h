@@ -90,6 +90,12 @@ void orc_sample(const orc_slot *slots, int n, const orc_camera *cam, uint64_t se
 void orc_render(const orc_slot *slots, int n, const orc_camera *cam, uint64_t seed,
                 int row0, int row1, float *out, uint64_t *segments);
 
+/* Analysis aid: record the ray segments of the following orc_sample / orc_render calls, 9 floats each
+ * {o.xyz, d.xyz, t or inf, slot id or -1, depth}; NULL stops recording.  orc_logged_segments counts all of them,
+ * also those beyond `capacity`. */
+void orc_log_segments(float *buf, long capacity);
+long orc_logged_segments(void);
+
 /* GF main.cu:366-377 quantisation of one gamma-encoded channel */
 int  orc_quantise(float x);
 
