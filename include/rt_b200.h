@@ -80,6 +80,10 @@ typedef struct rt_camera64 {
 
 enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
 enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2 };   /* AUTO: LBVH for float scenes with >= 256 slots */
+/* EXPERIMENTAL, refused (RT_EINVAL) unless the environment has RT_ENABLE_GRID=1: uniform grid over the ground plane for
+ * fields of equal spheres (csrc/rt_grid.cuh).  The algorithm is checked on the CPU (tests/test_grid_model.py); the kernel has
+ * not run on hardware yet.  Never chosen by RT_ACCEL_AUTO. */
+enum { RT_ACCEL_GRID = 4 };
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 enum { RT_PBINS_AUTO = 0, RT_PBINS_OFF = 1, RT_PBINS_ON = 2 };   /* AUTO: on wherever it applies */
 

@@ -203,6 +203,7 @@ def ppm_quantise(rgb):
 
 
 ACCEL_LINEAR, ACCEL_LBVH, ACCEL_AUTO = 0, 1, 2
+ACCEL_GRID = 4          # experimental (csrc/rt_grid.cuh): refused unless RT_ENABLE_GRID=1 is in the environment
 KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
 PBINS_AUTO, PBINS_OFF, PBINS_ON = 0, 1, 2
 

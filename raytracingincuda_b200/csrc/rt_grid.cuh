@@ -1,0 +1,106 @@
+// rt_grid.cuh -- uniform-grid closest hit for fields of equal spheres on a plane (the reference's scenes, BASELINE configs
+// 2-5).  EXPERIMENTAL in round 1: the algorithm is validated on the CPU against the oracle (tools/grid_model.py states it in
+// float32 operation by operation, tests/test_grid_model.py checks it on logged path segments), this CUDA transcription has
+// been compiled but not yet run on a GPU -- RT_ACCEL_GRID is refused unless RT_ENABLE_GRID=1 is set (rt_kernels.cu).
+//
+// A 2-D grid over the two long axes of the small spheres holds, per cell, the slots whose padded footprint overlaps the
+// cell; a ray walks the cells of its projection (Amanatides-Woo) inside the inflated box of those spheres and runs the
+// reference's exact sphere test (bvh_test_sphere) on what the cells list; spheres of a very different size (the ground, the
+// three big ones, the zero-radius slot) are tested for every ray.  tools/analyse_accel.py: 1.3 cells per scattered segment on
+// scene 1 and on the 99 860-slot scene alike, where the LBVH makes 6-13 node visits.
+// Conservativeness (same argument as tools/grid_model.py): a sphere can only be hit if the ray passes within r + delta of its
+// centre, delta = sqrt(rmin^2 + KEPS D^2) - rmin; footprints are registered with pad = 0.05 h; rays with delta <= pad / 2 walk
+// the thin line, rays with a larger delta (origins hundreds of units away) also look at k rings of cells around it; the
+// walk stops after a cell whose exit parameter lies beyond the closest hit so far.
+#pragma once
+#include "rt_lbvh.cuh"
+
+namespace rt {
+
+struct GridView {
+    const unsigned int *start;    // [nu * nw + 1] first item of each cell
+    const unsigned int *items;    // slots, cell by cell
+    const float4 *big_geom;       // spheres outside the grid: tested for every ray
+    const int *big_slot;
+    int nbig;
+    int nu, nw;
+    int au, av, aw;               // axis numbers of the grid's u, of the slab, of the grid's w
+    float lo[3], hi[3];           // bounds of the grid spheres (centre -/+ radius), rounded outwards, in x y z order
+    float h, inv_h, pad, rmin;
+};
+
+__constant__ GridView g_grid;     // one grid per device (set by the launch that uses it)
+
+__device__ __forceinline__ float axis_of(const Vec3<float> &v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// closest hit of one ray; `sc.geom` is the scene's geometry by slot (global memory)
+__device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const float4 *__restrict__ geom, const Vec3<float> &o,
+                                                       const Vec3<float> &d, unsigned &n_cells, unsigned &n_tests) {
+    using N = Num<float>;
+    const float inf = N::inf();
+    Hit<float> hit;
+    hit.t = inf;
+    hit.id = -1;
+    const float a = dot3(d, d);
+    for (int b = 0; b < g.nbig; ++b) bvh_test_sphere(__ldg(g.big_geom + b), __ldg(g.big_slot + b), o, d, a, hit);
+    n_tests += g.nbig;
+    // per-ray inflation, as bvh_start<true>
+    const float fx = fmaxf(fabsf(g.lo[0] - o.x), fabsf(g.hi[0] - o.x));
+    const float fy = fmaxf(fabsf(g.lo[1] - o.y), fabsf(g.hi[1] - o.y));
+    const float fz = fmaxf(fabsf(g.lo[2] - o.z), fabsf(g.hi[2] - o.z));
+    const float D2 = fz * fz + (fy * fy + fx * fx);
+    const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), fmx = fmaxf(fmaxf(fx, fy), fz);
+    const float root = sqrt_approx(BVH_KEPS * D2 + g.rmin * g.rmin) * (1.0f + 2e-7f);
+    const float delta = ((root - g.rmin) * 1.001f + 1e-7f) + 4.8e-7f * (omax + fmx);
+    const float half_pad = g.pad * 0.5f;
+    const int k = delta <= half_pad ? 0 : (int)fminf(ceilf((delta - half_pad) / g.h), 8192.0f) + 1;       // NaN -> 0 + 1
+    const float infl = delta + 1e-6f * (omax + fmx);
+    // clip to the inflated box of the grid spheres; |1/d| <= 1e30 keeps every product finite
+    Vec3<float> inv;
+    inv.x = d.x != 0.0f ? fminf(fmaxf(1.0f / d.x, -1e30f), 1e30f) : 1e30f;
+    inv.y = d.y != 0.0f ? fminf(fmaxf(1.0f / d.y, -1e30f), 1e30f) : 1e30f;
+    inv.z = d.z != 0.0f ? fminf(fmaxf(1.0f / d.z, -1e30f), 1e30f) : 1e30f;
+    float t0 = 0.0f, t1 = hit.t;
+    {
+        const float ax = ((g.lo[0] - infl) - o.x) * inv.x, bx = ((g.hi[0] + infl) - o.x) * inv.x;
+        const float ay = ((g.lo[1] - infl) - o.y) * inv.y, by = ((g.hi[1] + infl) - o.y) * inv.y;
+        const float az = ((g.lo[2] - infl) - o.z) * inv.z, bz = ((g.hi[2] + infl) - o.z) * inv.z;
+        t0 = fmaxf(fmaxf(t0, fminf(ax, bx)), fmaxf(fminf(ay, by), fminf(az, bz)));
+        t1 = fminf(fminf(t1, fmaxf(ax, bx)), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+    }
+    if (!(t0 <= t1 * 1.0001f + 1e-6f)) return hit;
+    t0 = fmaxf(0.0f, t0 - 1e-4f * fabsf(t0) - 1e-6f);
+    const float ou = axis_of(o, g.au), ow = axis_of(o, g.aw), du = axis_of(d, g.au), dw = axis_of(d, g.aw);
+    const float iu_inv = axis_of(inv, g.au), iw_inv = axis_of(inv, g.aw);
+    const float ulo = g.lo[g.au], wlo = g.lo[g.aw];
+    const float pu = ou + du * t0, pw = ow + dw * t0;
+    // walking indices are not clamped (the inflated clip box reaches a little beyond the grid); look-ups are
+    int iu = (int)fminf(fmaxf(floorf((pu - ulo) * g.inv_h), -65536.0f), 65536.0f);
+    int iw = (int)fminf(fmaxf(floorf((pw - wlo) * g.inv_h), -65536.0f), 65536.0f);
+    const int su = du > 0.0f ? 1 : (du < 0.0f ? -1 : 0), sw = dw > 0.0f ? 1 : (dw < 0.0f ? -1 : 0);
+    const int max_steps = 2 * (g.nu + g.nw) + 64;
+#pragma unroll 1
+    for (int step = 0; step < max_steps; ++step) {
+        ++n_cells;
+        const int cu = min(max(iu, 0), g.nu - 1), cw = min(max(iw, 0), g.nw - 1);
+        for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
+            for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {
+                const int cell = b * g.nu + c;
+                const unsigned int e0 = __ldg(g.start + cell), e1 = __ldg(g.start + cell + 1);
+                for (unsigned int e = e0; e < e1; ++e) {
+                    const int slot = (int)__ldg(g.items + e);
+                    bvh_test_sphere(__ldg(geom + slot), slot, o, d, a, hit);
+                }
+                n_tests += e1 - e0;
+            }
+        // exit parameters of the current cell, recomputed from the cell index (no accumulated drift)
+        const float tu = su == 0 ? inf : ((ulo + (float)(iu + (su > 0 ? 1 : 0)) * g.h) - ou) * iu_inv;
+        const float tw = sw == 0 ? inf : ((wlo + (float)(iw + (sw > 0 ? 1 : 0)) * g.h) - ow) * iw_inv;
+        const float t_exit = fminf(tu, tw), stop = fminf(hit.t, t1);
+        if (!(t_exit <= stop * 1.0001f + 1e-6f)) break;
+        if (tu <= tw) iu += su; else iw += sw;
+    }
+    return hit;
+}
+
+}  // namespace rt

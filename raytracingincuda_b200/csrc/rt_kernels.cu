@@ -16,6 +16,7 @@
 #include "rt_b200.h"
 #include "rt_device.cuh"
 #include "rt_lbvh.cuh"
+#include "rt_grid.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -541,6 +542,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
         d.z = N::sub(N::fma(fj, cam.dv.z, N::fma(fi, cam.du.z, cam.pixel00.z)), cam.center.z);
         Hit<T> hit;
         if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(bvh, cam.center, d, n_nodes, n_tests);
+        else if constexpr (ACCEL == RT_ACCEL_GRID && sizeof(T) == 4)
+            hit = grid_closest_hit(g_grid, static_cast<const float4 *>(scene.base), cam.center, d, n_nodes, n_tests);
         else hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
         if (valid) {
             ids[k] = hit.id;
@@ -671,6 +674,10 @@ struct rt_ctx {
     // wavefront variant: path pool
     void *wf_mem = nullptr;
     size_t wf_bytes = 0;
+    // uniform grid (RT_ACCEL_GRID, experimental): built on the host the first time it is asked for
+    bool grid_ready = false, grid_usable = false;
+    GridView grid{};
+    void *grid_mem[4] = {nullptr, nullptr, nullptr, nullptr};   // start, items, big_geom, big_slot
     // per-tile candidate lists of the camera rays (rt_primary_bins.cuh), rebuilt by every render call
     void *bins = nullptr;
     size_t bins_bytes = 0;
@@ -837,6 +844,9 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     for (void *&m : ctx->bvh_mem) if (m) { cudaFree(m); m = nullptr; }
     ctx->bvh_ready = false;
     ctx->bvh = BvhView{};
+    for (void *&m : ctx->grid_mem) if (m) { cudaFree(m); m = nullptr; }
+    ctx->grid_ready = ctx->grid_usable = false;
+    ctx->grid = GridView{};
     ctx->host_geom.clear();
     if (sizeof(T) == 4) {
         ctx->host_geom.resize((size_t)n);
@@ -984,6 +994,109 @@ int build_lbvh(rt_ctx *ctx) {
     return RT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Uniform grid (rt_grid.cuh), host build; mirrors tools/grid_model.py (class Grid).  Sets ctx->grid_usable = false for scenes
+// the structure does not fit (fewer than two similar spheres, more than 64 spheres of a very different size).
+int build_grid(rt_ctx *ctx) {
+    if (ctx->grid_ready) return RT_OK;
+    if (ctx->scene_prec != 4 || ctx->host_geom.empty()) return RT_EPRECISION;
+    const std::vector<float4> &g = ctx->host_geom;
+    const int n = (int)g.size();
+    std::vector<double> rad;
+    for (const float4 &s : g) {
+        const double r = std::fabs((double)s.w);
+        if (std::isfinite(s.x) && std::isfinite(s.y) && std::isfinite(s.z) && std::isfinite(r) && r > 0.0) rad.push_back(r);
+    }
+    double r_med = 0.0;
+    if (!rad.empty()) { std::sort(rad.begin(), rad.end()); r_med = rad.size() % 2 ? rad[rad.size() / 2] : 0.5 * (rad[rad.size() / 2 - 1] + rad[rad.size() / 2]); }
+    std::vector<int> in_grid, big;
+    for (int i = 0; i < n; ++i) {
+        const float4 &s = g[(size_t)i];
+        const double r = std::fabs((double)s.w);
+        const bool fin = std::isfinite(s.x) && std::isfinite(s.y) && std::isfinite(s.z) && std::isfinite(r);
+        ((fin && r > 0.0 && r >= 0.25 * r_med && r <= 4.0 * r_med) ? in_grid : big).push_back(i);
+    }
+    ctx->grid_ready = true;
+    ctx->grid_usable = in_grid.size() >= 2 && big.size() <= 64;
+    if (!ctx->grid_usable) return RT_OK;
+    double cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double r_max = 0.0, r_min = INFINITY;
+    for (int i : in_grid) {
+        const float4 &s = g[(size_t)i];
+        const double c[3] = {s.x, s.y, s.z}, r = std::fabs((double)s.w);
+        for (int q = 0; q < 3; ++q) {
+            cmin[q] = std::min(cmin[q], c[q]); cmax[q] = std::max(cmax[q], c[q]);
+            lo3[q] = std::min(lo3[q], c[q] - r); hi3[q] = std::max(hi3[q], c[q] + r);
+        }
+        r_max = std::max(r_max, r); r_min = std::min(r_min, r);
+    }
+    int av = 0;
+    for (int q = 1; q < 3; ++q) if (cmax[q] - cmin[q] < cmax[av] - cmin[av]) av = q;
+    const int au = av == 0 ? 1 : 0, aw = av == 2 ? 1 : 2;
+    const double eu = hi3[au] - lo3[au], ew = hi3[aw] - lo3[aw];
+    double h = std::sqrt(std::max(eu * ew, 1e-30) / (double)in_grid.size());
+    h = std::max(h, r_max);
+    const int nu = (int)std::min(std::max(std::ceil(eu / h), 1.0), 4096.0), nw = (int)std::min(std::max(std::ceil(ew / h), 1.0), 4096.0);
+    h = std::max(std::max(eu / nu, ew / nw), h);
+    GridView G{};
+    G.nu = nu; G.nw = nw; G.au = au; G.av = av; G.aw = aw;
+    G.h = (float)(h * (1.0 + 1e-6));
+    G.inv_h = 1.0f / G.h;
+    for (int q = 0; q < 3; ++q) { G.lo[q] = std::nextafter((float)lo3[q], -INFINITY); G.hi[q] = std::nextafter((float)hi3[q], INFINITY); }
+    G.rmin = (float)r_min;
+    G.pad = (float)(0.05 * (double)G.h);
+    const double hh = G.h, ulo = G.lo[au], wlo = G.lo[aw];
+    std::vector<unsigned int> count((size_t)nu * nw + 1, 0u);
+    auto range = [&](double c, double R, double base, int cells, int &a0, int &a1) {
+        a0 = (int)std::min(std::max(std::floor((c - R - base) / hh), 0.0), (double)(cells - 1));
+        a1 = (int)std::min(std::max(std::floor((c + R - base) / hh), 0.0), (double)(cells - 1));
+    };
+    std::vector<unsigned int> items, fill;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            unsigned int run = 0;
+            for (size_t k = 0; k < count.size(); ++k) { const unsigned int c = count[k]; count[k] = run; run += c; }   // exclusive scan
+            items.assign(run, 0u);
+            fill.assign(count.begin(), count.end());
+        }
+        for (int i : in_grid) {
+            const float4 &s = g[(size_t)i];
+            const double c[3] = {s.x, s.y, s.z};
+            const double R = (std::fabs((double)s.w) + (double)G.pad) * (1.0 + 1e-6);
+            int u0, u1, w0, w1;
+            range(c[au], R, ulo, nu, u0, u1);
+            range(c[aw], R, wlo, nw, w0, w1);
+            for (int b = w0; b <= w1; ++b)
+                for (int a = u0; a <= u1; ++a) {
+                    const size_t cell = (size_t)b * nu + a;
+                    if (pass == 0) ++count[cell];
+                    else items[fill[cell]++] = (unsigned int)i;
+                }
+        }
+        if (pass == 1) {
+            std::vector<float4> bg(big.size());
+            for (size_t b = 0; b < big.size(); ++b) bg[b] = g[(size_t)big[b]];
+            RT_CUDA(cudaMalloc(&ctx->grid_mem[0], count.size() * sizeof(unsigned int)));
+            RT_CUDA(cudaMalloc(&ctx->grid_mem[1], std::max<size_t>(items.size(), 1) * sizeof(unsigned int)));
+            RT_CUDA(cudaMalloc(&ctx->grid_mem[2], std::max<size_t>(bg.size(), 1) * sizeof(float4)));
+            RT_CUDA(cudaMalloc(&ctx->grid_mem[3], std::max<size_t>(big.size(), 1) * sizeof(int)));
+            RT_CUDA(cudaMemcpyAsync(ctx->grid_mem[0], count.data(), count.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+            if (!items.empty()) RT_CUDA(cudaMemcpyAsync(ctx->grid_mem[1], items.data(), items.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+            if (!bg.empty()) RT_CUDA(cudaMemcpyAsync(ctx->grid_mem[2], bg.data(), bg.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            if (!big.empty()) RT_CUDA(cudaMemcpyAsync(ctx->grid_mem[3], big.data(), big.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RT_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    G.start = static_cast<const unsigned int *>(ctx->grid_mem[0]);
+    G.items = static_cast<const unsigned int *>(ctx->grid_mem[1]);
+    G.big_geom = static_cast<const float4 *>(ctx->grid_mem[2]);
+    G.big_slot = static_cast<const int *>(ctx->grid_mem[3]);
+    G.nbig = (int)big.size();
+    ctx->grid = G;
+    return RT_OK;
+}
+
 // RT_ACCEL_AUTO -> the faster structure for this scene (same image either way)
 int resolve_accel(const rt_ctx *ctx, int accel) {
     if (accel != RT_ACCEL_AUTO) return accel;
@@ -1093,6 +1206,15 @@ int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_loca
     return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
 }
 
+// RT_ACCEL_GRID (experimental, float): camera rays through the tile lists, scattered rays through the uniform grid.
+template <typename T, typename Cam> struct GridImpl {
+    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, int, typename Num<T>::vec4 *) { return RT_EPRECISION; }
+};
+template <typename T, typename Cam>
+int trace_grid(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, typename Num<T>::vec4 *partial) {
+    return GridImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
+}
+
 // The LBVH is a float structure: these helpers keep the double instantiation of trace() from naming float-only kernels
 // (trace() rejects double + LBVH before it gets here).
 inline void launch_bins_bvh(const DevCamera<float> &cam, const BvhView &bv, int w, int h, int tx, int ty, unsigned int *bins, unsigned grid,
@@ -1108,11 +1230,72 @@ template <typename T, int ACCEL> int shape_pb(rt_ctx *ctx, size_t smem, int *gri
     else return RT_EPRECISION;
 }
 
+template <typename Cam> struct GridImpl<float, Cam> {
+    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, float4 *partial) {
+        int rc = build_grid(ctx);
+        if (rc) return rc;
+        if (!ctx->grid_usable) return RT_EINVAL;                    // not a field of similar spheres: use RT_ACCEL_LBVH
+        int grid = 0;
+        rc = launch_shape(ctx, trace_kernel_pb<float, RT_ACCEL_GRID>, 0, &grid);
+        if (rc) return rc;
+        TraceArgs<float> A;
+        A.bvh = BvhView{};
+        A.bvh_steps = 0;
+        A.bvh_min_active = 0;
+        A.pb_rounds = 3;
+        A.pb_min = 1;
+        A.cam = to_dev<float>(cam);
+        A.scene = ctx->blob;
+        A.keys = philox_keys(o.seed);
+        A.spp = cam.spp; A.max_depth = cam.max_depth;
+        A.width = cam.width;
+        A.tile_rows = o.tile_rows; A.rank = o.rank;
+        A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
+        A.chunks = chunks; A.c_begin = c0;
+        A.spp_q = cam.spp / chunks; A.spp_r = cam.spp % chunks;
+        A.pix_local = (unsigned long long)rows_local * cam.width;
+        A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
+        A.magic_pix = A.pix_local > 1 ? ~0ull / A.pix_local + 1ull : 0ull;
+        A.magic_width = cam.width > 1 ? ~0ull / (unsigned long long)cam.width + 1ull : 0ull;
+        A.partial = partial;
+        A.queue = ctx->queue;
+        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
+        if (A.total_jobs == 0) return RT_OK;
+        const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
+        if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        ctx->stats.grid = grid;
+        const int tiles_x = (cam.width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (cam.height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
+        const size_t tiles = (size_t)tiles_x * tiles_y;
+        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned int));
+        if (rc) return rc;
+        unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
+        A.bins = bins;
+        A.tiles_x = tiles_x;
+        const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
+        if (ctx->blob.n > 8192) {
+            // large scenes: the tile lists come from a walk of the LBVH (one thread per tile cannot loop over 10^5 slots)
+            rc = build_lbvh(ctx);
+            if (rc) return rc;
+            bin_kernel_bvh<<<bin_grid, 128, 0, ctx->stream>>>(A.cam, ctx->bvh, cam.width, cam.height, tiles_x, tiles_y, bins);
+        } else {
+            bin_kernel<float><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const float4 *>(ctx->blob.base), ctx->blob.n,
+                                                                cam.width, cam.height, tiles_x, tiles_y, bins);
+        }
+        RT_CUDA(cudaGetLastError());
+        RT_CUDA(cudaMemcpyToSymbolAsync(g_grid, &ctx->grid, sizeof(GridView), 0, cudaMemcpyHostToDevice, ctx->stream));
+        trace_kernel_pb<float, RT_ACCEL_GRID><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(A);
+        RT_CUDA(cudaGetLastError());
+        ctx->stats.launches += 2;
+        return RT_OK;
+    }
+};
+
 // Launches the path tracer for chunks [c0,c1) over `rows_local` rows into `partial`.
 template <typename T, typename Cam>
 int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
           typename Num<T>::vec4 *partial) {
     if (o.kernel == RT_KERNEL_WAVEFRONT) return trace_wavefront<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
+    if (o.accel == RT_ACCEL_GRID) return trace_grid<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
     const bool lbvh = (resolve_accel(ctx, o.accel) == RT_ACCEL_LBVH);
     if (lbvh && sizeof(T) != 4) return RT_EPRECISION;
     const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
@@ -1206,7 +1389,10 @@ int check_opts(const rt_opts &o) {
     if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return RT_EINVAL;
     if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
-    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO) return RT_EINVAL;
+    const bool grid_enabled = getenv("RT_ENABLE_GRID") != nullptr;              // experimental, see rt_grid.cuh
+    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO && !(o.accel == RT_ACCEL_GRID && grid_enabled))
+        return RT_EINVAL;
+    if (o.accel == RT_ACCEL_GRID && (o.kernel != RT_KERNEL_MEGA || o.primary_bins == RT_PBINS_OFF)) return RT_EINVAL;
     if (o.kernel != RT_KERNEL_MEGA && o.kernel != RT_KERNEL_WAVEFRONT) return RT_EINVAL;
     if (o.primary_bins < RT_PBINS_AUTO || o.primary_bins > RT_PBINS_ON) return RT_EINVAL;
     if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel == RT_ACCEL_LBVH) return RT_EINVAL;
@@ -1289,10 +1475,18 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
     return RT_OK;
 }
 
+inline void launch_primary_grid(const DevCamera<float> &cam, const SceneBlob &scene, const BvhView &bvh, int w, int h, int32_t *ids, float *t,
+                                int grid_dim, cudaStream_t st) {
+    primary_kernel<float, RT_ACCEL_GRID><<<grid_dim, TRACE_BLOCK, 0, st>>>(cam, scene, bvh, w, h, ids, t);
+}
+inline void launch_primary_grid(const DevCamera<double> &, const SceneBlob &, const BvhView &, int, int, int32_t *, double *, int, cudaStream_t) {}
+
 template <typename T, typename Cam>
 int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (!ctx || !cam || !ids || !t) return RT_EINVAL;
-    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH && accel != RT_ACCEL_AUTO) return RT_EINVAL;
+    const bool grid = accel == RT_ACCEL_GRID && getenv("RT_ENABLE_GRID") != nullptr;       // experimental, see rt_grid.cuh
+    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH && accel != RT_ACCEL_AUTO && !grid) return RT_EINVAL;
+    if (grid && sizeof(T) != 4) return RT_EPRECISION;
     if (ctx) accel = resolve_accel(ctx, accel);
     if (accel == RT_ACCEL_LBVH && sizeof(T) != 4) return RT_EPRECISION;
     if (!ctx->scene_dev) return RT_ENOSCENE;
@@ -1309,21 +1503,29 @@ int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
         if (!ids_dev) d_ids = reinterpret_cast<int32_t *>(static_cast<char *>(tmp) + npix * sizeof(T));
     }
     const bool lbvh = accel == RT_ACCEL_LBVH;
-    const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
+    const size_t smem = (lbvh || grid) ? 0 : trace_smem(ctx->blob);
     int rc = RT_OK;
-    if (!lbvh && (smem > 227 * 1024 || ctx->blob.n > 65535)) rc = RT_EINVAL;
+    if (!lbvh && !grid && (smem > 227 * 1024 || ctx->blob.n > 65535)) rc = RT_EINVAL;
     if (rc == RT_OK && lbvh) rc = build_lbvh(ctx);
+    if (rc == RT_OK && grid) {
+        rc = build_grid(ctx);
+        if (rc == RT_OK && !ctx->grid_usable) rc = RT_EINVAL;
+        if (rc == RT_OK && cudaMemcpyToSymbolAsync(g_grid, &ctx->grid, sizeof(GridView), 0, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+            rc = (int)cudaGetLastError();
+    }
     if (rc != RT_OK) { if (tmp) cudaFree(tmp); return rc; }
-    cudaError_t e = lbvh ? cudaSuccess
+    cudaError_t e = (lbvh || grid) ? cudaSuccess
                          : cudaFuncSetAttribute(primary_kernel<T, RT_ACCEL_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        int grid = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
-        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-        if (lbvh)
-            primary_kernel<T, RT_ACCEL_LBVH><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width,
-                                                                                    cam->height, d_ids, d_t);
+        int grid_dim = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        if (grid_dim > ctx->sm_count * 8) grid_dim = ctx->sm_count * 8;
+        if (grid)
+            launch_primary_grid(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width, cam->height, d_ids, d_t, grid_dim, ctx->stream);
+        else if (lbvh)
+            primary_kernel<T, RT_ACCEL_LBVH><<<grid_dim, TRACE_BLOCK, 0, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width,
+                                                                                        cam->height, d_ids, d_t);
         else
-            primary_kernel<T, RT_ACCEL_LINEAR><<<grid, TRACE_BLOCK, smem, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh,
+            primary_kernel<T, RT_ACCEL_LINEAR><<<grid_dim, TRACE_BLOCK, smem, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh,
                                                                                          cam->width, cam->height, d_ids, d_t);
         e = cudaGetLastError();
     }
@@ -1374,6 +1576,7 @@ int rt_destroy(rt_ctx *ctx) {
     for (void *m : ctx->bvh_mem) if (m) cudaFree(m);
     if (ctx->wf_mem) cudaFree(ctx->wf_mem);
     if (ctx->bins) cudaFree(ctx->bins);
+    for (void *m : ctx->grid_mem) if (m) cudaFree(m);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

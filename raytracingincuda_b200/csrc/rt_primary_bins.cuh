@@ -206,13 +206,14 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     using N = Num<T>;
     constexpr bool LB = (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT);
     constexpr bool RAYD = (ACCEL == ACCEL_LBVH_COMPACT);
-    static_assert(!LB || sizeof(T) == 4, "the LBVH is a float structure");
+    constexpr bool GR = (ACCEL == RT_ACCEL_GRID);                  // experimental uniform grid (rt_grid.cuh)
+    static_assert(!(LB || GR) || sizeof(T) == 4, "the LBVH and the grid are float structures");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     SceneView<T> sc;
     unsigned short *cand = nullptr;
     ScanGeom geo = scan_geom(0u, 0);
-    if constexpr (!LB) {
+    if constexpr (!LB && !GR) {
         stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
         sc = view_of<T>(smem, A.scene);
         cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
@@ -313,7 +314,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                         // the record is consumed one word at a time: rotate the 128-bit window, refill every 4 entries
                         if ((e & 3u) == 0u) q = __ldg(rec + (e >> 2));
                         else { q.x = q.y; q.y = q.z; q.z = q.w; }
-                        if constexpr (LB) bvh_test_sphere(__ldg(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
+                        if constexpr (LB || GR) bvh_test_sphere(__ldg(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
                         else resolve_slot<T>(geo.addr, (int)q.x, ps.o, ps.d, a, h);
                     }
                     n_tests += cnt;
@@ -347,6 +348,9 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                 if (tv.node >= 0) bvh_step<RAYD>(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
             }
             if (state == ACTIVE && phase == FLY && tv.node < 0) land(tv.hit);
+        } else if constexpr (GR) {
+            // a grid walk is short (1.3 cells on average, tools/analyse_accel.py): it runs to the end right here
+            if (state == ACTIVE && phase == RAY) land(grid_closest_hit(g_grid, sc.geom, ps.o, ps.d, n_nodes, n_tests));
         } else {
             // all 32 lanes take part in the shared-memory scan; the ones without a live ray scan a stale one
             const bool scan = (state == ACTIVE && phase == RAY);
@@ -369,7 +373,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
         atomicAdd(A.queue + 2, pth);
         atomicAdd(A.queue + 5, bnd);
     }
-    if constexpr (LB) {
+    if constexpr (LB || GR) {
         unsigned long long nod = n_nodes, tst = n_tests;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
