@@ -1,7 +1,9 @@
 // rt_grid.cuh -- uniform-grid closest hit for fields of equal spheres on a plane (the reference's scenes, BASELINE configs
 // 2-5).  EXPERIMENTAL in round 1: the algorithm is validated on the CPU against the oracle (tools/grid_model.py states it in
 // float32 operation by operation, tests/test_grid_model.py checks it on logged path segments), this CUDA transcription has
-// been compiled but not yet run on a GPU -- RT_ACCEL_GRID is refused unless RT_ENABLE_GRID=1 is set (rt_kernels.cu).
+// has had ONE hardware run (round 1, commit "RT_ACCEL_GRID (experimental ...": 9 gated parity tests green, scene 1 at config 2
+// 49.3 ms against 57.7 ms through the LBVH, but 225 ms against 47 ms on the 99 860-slot scene); the per-step inflation below
+// was added after that run and has only been checked in the model -- RT_ACCEL_GRID stays refused unless RT_ENABLE_GRID=1.
 //
 // A 2-D grid over the two long axes of the small spheres holds, per cell, the slots whose padded footprint overlaps the
 // cell; a ray walks the cells of its projection (Amanatides-Woo) inside the inflated box of those spheres and runs the
@@ -10,8 +12,8 @@
 // scene 1 and on the 99 860-slot scene alike, where the LBVH makes 6-13 node visits.
 // Conservativeness (same argument as tools/grid_model.py): a sphere can only be hit if the ray passes within r + delta of its
 // centre, delta = sqrt(rmin^2 + KEPS D^2) - rmin; footprints are registered with pad = 0.05 h; rays with delta <= pad / 2 walk
-// the thin line, rays with a larger delta (origins hundreds of units away) also look at k rings of cells around it; the
-// walk stops after a cell whose exit parameter lies beyond the closest hit so far.
+// the thin line, steps with a larger delta (cells hundreds of units from the origin) also look at k rings of cells around
+// it; the walk stops after a cell whose exit parameter lies beyond the closest hit so far.
 #pragma once
 #include "rt_lbvh.cuh"
 
@@ -53,7 +55,7 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
     const float root = sqrt_approx(BVH_KEPS * D2 + g.rmin * g.rmin) * (1.0f + 2e-7f);
     const float delta = ((root - g.rmin) * 1.001f + 1e-7f) + 4.8e-7f * (omax + fmx);
     const float half_pad = g.pad * 0.5f;
-    const int k = delta <= half_pad ? 0 : (int)fminf(ceilf((delta - half_pad) / g.h), 8192.0f) + 1;       // NaN -> 0 + 1
+    const int k_global = delta <= half_pad ? 0 : (int)fminf(ceilf((delta - half_pad) / g.h), 8192.0f) + 1;       // NaN -> 0 + 1
     const float infl = delta + 1e-6f * (omax + fmx);
     // clip to the inflated box of the grid spheres; |1/d| <= 1e30 keeps every product finite
     Vec3<float> inv;
@@ -79,9 +81,21 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
     int iw = (int)fminf(fmaxf(floorf((pw - wlo) * g.inv_h), -65536.0f), 65536.0f);
     const int su = du > 0.0f ? 1 : (du < 0.0f ? -1 : 0), sw = dw > 0.0f ? 1 : (dw < 0.0f ? -1 : 0);
     const int max_steps = 2 * (g.nu + g.nw) + 64;
+    const float length = sqrtf(a);
 #pragma unroll 1
     for (int step = 0; step < max_steps; ++step) {
         ++n_cells;
+        // exit parameters of the current cell, recomputed from the cell index (no accumulated drift)
+        const float tu = su == 0 ? inf : ((ulo + (float)(iu + (su > 0 ? 1 : 0)) * g.h) - ou) * iu_inv;
+        const float tw = sw == 0 ? inf : ((wlo + (float)(iw + (sw > 0 ? 1 : 0)) * g.h) - ow) * iw_inv;
+        // Inflation of THIS step: a sphere whose root lies in the current cell is at most t_far |d| + 2 h + delta away from
+        // the origin (t_far: where the ray leaves the cell or the walk ends).  With the one inflation per ray of the first
+        // version (evaluated at the far corner of the grid) every step of the 99 860-slot scene looked at two rings of cells.
+        const float t_far = fminf(fminf(tu, tw), t1);
+        const float Ds = (t_far * length) * 1.0001f + (2.0f * g.h + delta);
+        const float rs = sqrt_approx(BVH_KEPS * (Ds * Ds) + g.rmin * g.rmin) * (1.0f + 2e-7f);
+        const float ds = ((rs - g.rmin) * 1.001f + 1e-7f) + 4.8e-7f * (omax + Ds);
+        const int k = ds <= half_pad ? 0 : min((int)fminf(ceilf((ds - half_pad) / g.h), 8192.0f) + 1, k_global);
         const int cu = min(max(iu, 0), g.nu - 1), cw = min(max(iw, 0), g.nw - 1);
         for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
             for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {
@@ -93,9 +107,6 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
                 }
                 n_tests += e1 - e0;
             }
-        // exit parameters of the current cell, recomputed from the cell index (no accumulated drift)
-        const float tu = su == 0 ? inf : ((ulo + (float)(iu + (su > 0 ? 1 : 0)) * g.h) - ou) * iu_inv;
-        const float tw = sw == 0 ? inf : ((wlo + (float)(iw + (sw > 0 ? 1 : 0)) * g.h) - ow) * iw_inv;
         const float t_exit = fminf(tu, tw), stop = fminf(hit.t, t1);
         if (!(t_exit <= stop * 1.0001f + 1e-6f)) break;
         if (tu <= tw) iu += su; else iw += sw;

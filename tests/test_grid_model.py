@@ -57,6 +57,7 @@ SCENES = {
     "scene1": (lambda: O.scene(1), 400), "scene2": (lambda: O.scene(2), 300), "scene3": (lambda: O.scene(3), 300),
     "shifted": (lambda: moved(O.scene(1), 1.0, (37.0, 3.0, -21.0)), 300),
     "scaled24": (lambda: O.scene_scaled(24), 150),
+    "scaled100": (lambda: O.scene_scaled(100), 60),       # 40 004 slots, 200 cells wide: far cells need rings, near ones do not
 }
 
 
@@ -82,8 +83,28 @@ def test_grid_walk_finds_the_full_scan_hit(name):
             assert np.float32(t).view(np.uint32) == want_t.view(np.uint32)
         tested_total += len(tested)
         cells_total += cells
-    # the point of the structure: a handful of exact tests per segment
+    # the point of the structure: a handful of exact tests per segment, whatever the size of the scene
     assert tested_total / len(seg) < 6 and cells_total / len(seg) < 4, (tested_total / len(seg), cells_total / len(seg))
+
+
+def test_one_inflation_per_ray_is_exact_too_but_wasteful_on_large_grids():
+    """The variant that ran on hardware first (csrc/rt_grid.cuh in round 1): same hits, many more tests on a wide grid."""
+    slots = O.scene_scaled(100)
+    G = GM.Grid(slots)
+    seg = logged_segments(slots, O.camera(640, 360, 1000, 50), 25, seed=3)
+    tested = {True: 0, False: 0}
+    for row in seg:
+        o, d = row[0:3], row[3:6]
+        big_t, big_s = closest_among(slots, G.big, o, d)
+        res = {}
+        for local in (True, False):
+            t, s, used, _ = GM.candidates(G, o, d, big_t, lambda idx: closest_among(slots, idx, o, d), local=local)
+            if big_t < t or (big_t == t and big_s >= 0 and (s < 0 or big_s < s)):
+                t, s = big_t, big_s
+            res[local] = (np.float32(t).view(np.uint32), s)
+            tested[local] += len(used)
+        assert res[True] == res[False] and res[True][1] == int(row[7])
+    assert tested[False] > 4 * tested[True], tested
 
 
 def test_far_origins_widen_the_walk():
