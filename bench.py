@@ -59,7 +59,8 @@ def parse_args():
     ap.add_argument("--spp-combine", default="gather", choices=["gather", "reduce"],
                     help="spp split: ordered gather (bit-exact) or NCCL sum-reduce of the accumulation buffer")
     ap.add_argument("--tile-rows", type=int, default=1)
-    ap.add_argument("--accel", default="linear", choices=["linear", "lbvh"])
+    ap.add_argument("--accel", default="linear", choices=["linear", "lbvh", "grid"],
+                    help="grid: experimental (csrc/rt_grid.cuh), needs RT_ENABLE_GRID=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-lbvh-extra", action="store_true")
@@ -280,8 +281,9 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     scene_id, W, H, spp, depth = WORKLOADS[args.workload]
-    lbvh = scene_id < 0 or args.accel == "lbvh"
-    accel = api.ACCEL_LBVH if lbvh else api.ACCEL_LINEAR
+    grid_accel = args.accel == "grid"
+    lbvh = (scene_id < 0 or args.accel == "lbvh") and not grid_accel
+    accel = api.ACCEL_GRID if grid_accel else (api.ACCEL_LBVH if lbvh else api.ACCEL_LINEAR)
     slots = rt.scene_scaled(-scene_id) if scene_id < 0 else rt.scene(scene_id)
     cam = rt.camera(W, H, spp, depth)
     chunks = rt.num_chunks(W, H, spp)
@@ -392,7 +394,8 @@ def run_b200_arm(args):
         n_slots = len(slots)
         clk = clocks.summary()
         # linear scan: segments x slots tests; LBVH: the leaf/big tests the traversal actually made
-        flop = sphere_tests * FLOP_PER_TEST                             # whole job, one step
+        # (grid: the reference's algorithmic work as for the linear scan; the counted tests go into the note)
+        flop = (segments * n_slots if grid_accel else sphere_tests) * FLOP_PER_TEST      # whole job, one step
         achieved = flop / (step_trace_ms * 1e-3) / 1e12 / world         # per GPU (per launch of the trace kernel)
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
@@ -415,7 +418,9 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload),
-                       "implementation": "float, " + ("on-GPU LBVH" if lbvh else "linear scan in shared memory, camera rays "
+                       "implementation": "float, " + ("uniform grid over the ground plane (EXPERIMENTAL, RT_ENABLE_GRID=1), camera rays "
+                                                           "through per-tile candidate lists" if grid_accel else
+                                                           "on-GPU LBVH" if lbvh else "linear scan in shared memory, camera rays "
                                                            "through per-tile candidate lists (rt_opts.primary_bins)"),
                        "l2": "inputs regenerate per step; "
                                    f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else "nccl-gather"))) if world > 1 else "none",
@@ -425,7 +430,7 @@ def run_b200_arm(args):
                     "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
             "gpu_launches": timed_launches,
             "clocks": clk,
-            "roofline": roof if lbvh else {"bound": "fp32", "kernel": "trace_kernel_pb<float>", "achieved": round(achieved, 3),
+            "roofline": roof if lbvh else {"bound": "fp32", "kernel": "trace_kernel_pb<float,grid>" if grid_accel else "trace_kernel_pb<float>", "achieved": round(achieved, 3),
                          "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                          "frac_at_observed_clock": round(achieved / (peak * obs / sm_max), 4),
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks_src} MEASURED_PEAKS.json)",
@@ -437,6 +442,8 @@ def run_b200_arm(args):
                                   f"and scans the other {segments - binned_segments} with a 7-FMA conservative filter per test plus "
                                   "the exact test on the ~0.5 % candidates"),
                          "scanned_fraction": round((segments - binned_segments) / max(1, segments), 4),
+                         **({"grid": {"cells_per_segment": round(node_visits / max(1, segments), 3),
+                                      "exact_tests_per_segment": round(sphere_tests / max(1, segments), 3)}} if grid_accel else {}),
                          "kernel_ms": round(step_trace_ms, 3), "traffic": None},
         }
         # DRAM bytes per trace_kernel launch from the committed ncu pass over this same command

@@ -104,7 +104,11 @@ Args parse(int argc, char **argv) {
         else if (name == "gather") a.gather = value;
         else if (name == "scene_file") a.scene_file = value;
         else if (name == "dump_scene") a.dump_scene = value;
-        else if (name == "accel") { a.lbvh = (value == "lbvh"); a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : RT_ACCEL_LINEAR); }
+        else if (name == "accel") {
+            a.lbvh = (value == "lbvh");
+            // "grid": experimental uniform grid, refused by the library unless RT_ENABLE_GRID=1 (csrc/rt_grid.cuh)
+            a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : (value == "grid" ? RT_ACCEL_GRID : RT_ACCEL_LINEAR));
+        }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
         else if (name == "primary_bins") a.primary_bins = (value == "off") ? RT_PBINS_OFF : RT_PBINS_ON;
         else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
