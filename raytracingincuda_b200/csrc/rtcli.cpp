@@ -107,7 +107,7 @@ Args parse(int argc, char **argv) {
         else if (name == "accel") {
             a.lbvh = (value == "lbvh");
             // "grid": experimental uniform grid, refused by the library unless RT_ENABLE_GRID=1 (csrc/rt_grid.cuh)
-            a.accel = value == "lbvh" ? RT_ACCEL_LBVH : (value == "auto" ? RT_ACCEL_AUTO : (value == "grid" ? RT_ACCEL_GRID : RT_ACCEL_LINEAR));
+            a.accel = value == "lbvh" ? (int)RT_ACCEL_LBVH : (value == "auto" ? (int)RT_ACCEL_AUTO : (value == "grid" ? (int)RT_ACCEL_GRID : (int)RT_ACCEL_LINEAR));
         }
         else if (name == "kernel") a.wavefront = (value == "wavefront");
         else if (name == "primary_bins") a.primary_bins = (value == "off") ? RT_PBINS_OFF : RT_PBINS_ON;
