@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 enum {
     RT_OK = 0,
@@ -79,11 +79,15 @@ typedef struct rt_camera64 {
 } rt_camera64;
 
 enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
-enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2 };   /* AUTO: LBVH for float scenes with >= 256 slots */
-/* EXPERIMENTAL, refused (RT_EINVAL) unless the environment has RT_ENABLE_GRID=1: uniform grid over the ground plane for
- * fields of equal spheres (csrc/rt_grid.cuh).  The algorithm is checked on the CPU (tests/test_grid_model.py); the kernel has
- * not run on hardware yet.  Never chosen by RT_ACCEL_AUTO. */
-enum { RT_ACCEL_GRID = 4 };
+/* How hit_world (GF hittable.h:80-98) finds the closest hit.  Every choice returns the same (slot id, t) and therefore the
+ * same image, bit for bit; they differ in speed only.
+ *   LINEAR  the reference's linear scan, in shared memory (float and double scenes up to 65 535 slots);
+ *   LBVH    LBVH built on the device (float scenes of any size);
+ *   GRID    uniform grid over the two long axes of a field of similar spheres (float scenes; RT_EINVAL if the scene is not
+ *           such a field: fewer than two similar spheres or more than 64 of a very different size);
+ *   AUTO    (default) LINEAR below 256 slots, for double scenes and for the wavefront kernel; otherwise GRID when the
+ *           scene is a compact planar field of similar spheres (the reference's scenes), else LBVH. */
+enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2, RT_ACCEL_GRID = 4 };
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 enum { RT_PBINS_AUTO = 0, RT_PBINS_OFF = 1, RT_PBINS_ON = 2 };   /* AUTO: on wherever it applies */
 
@@ -93,7 +97,7 @@ typedef struct rt_opts {
     int32_t split;        /* RT_SPLIT_*: which part of the frame this context renders */
     int32_t rank, world;  /* this context's index / number of partitions (1 = whole frame) */
     int32_t tile_rows;    /* RT_SPLIT_ROWS: rows per interleaved tile (default 1: row j -> rank j mod world) */
-    int32_t accel;        /* RT_ACCEL_* */
+    int32_t accel;        /* RT_ACCEL_*; rt_opts_default sets RT_ACCEL_AUTO */
     int32_t threads;      /* the reference's --threads; accepted and ignored by the persistent kernel */
     int32_t kernel;       /* RT_KERNEL_*: persistent megakernel (default) or the material-sorted wavefront
                            * variant (float, linear scan); both produce the same image bit for bit */
@@ -108,16 +112,23 @@ typedef struct rt_opts {
 typedef struct rt_stats {
     uint64_t paths;          /* path-samples traced by the last render call on this context */
     uint64_t segments;       /* hit_world calls (ray segments) of the last render call */
-    uint64_t sphere_tests;   /* sphere tests (segments x slots for the linear scan; counted for LBVH) */
-    uint64_t node_visits;    /* LBVH node visits (0 for the linear scan) */
+    uint64_t sphere_tests;   /* EXACT sphere tests executed (the reference's discriminant, 12 FP32 instructions each): candidates of
+                              * the scan's filter, entries of the camera-ray lists, LBVH leaves, grid cell entries */
+    uint64_t node_visits;    /* LBVH node visits / grid cells visited (0 for the linear scan) */
     float render_ms;         /* CUDA-event time of the render kernels of the last call */
     float trace_ms;          /* ... of the path-tracing kernel alone */
     int32_t launches;        /* kernels launched by the last call */
-    int32_t chunks;          /* accumulation chunks of the last call */
+    int32_t chunks;          /* sample ranges (jobs) per pixel of the last call: scheduling only, the image does not depend on it */
     int32_t grid, block;     /* launch shape of the path-tracing kernel */
     int32_t regs, smem_bytes;
     uint64_t binned_segments; /* camera-ray segments resolved against their tile's candidate list instead of the scan
                                * (rt_opts.primary_bins); they are included in `segments` */
+    uint64_t filter_tests;    /* conservative 7-FMA filter tests the shared-memory scan executed (all 32 lanes of a scanning warp,
+                               * two rays per record); 0 for LBVH / grid */
+    float bvh_build_ms;       /* device time of the last LBVH build of this context (0 if none) */
+    float grid_build_ms;      /* host time of the last uniform-grid build of this context (0 if none) */
+    int32_t accel_used;       /* RT_ACCEL_* the last call resolved to (RT_ACCEL_AUTO never appears here) */
+    int32_t reserved;
 } rt_stats;
 
 /* ------------------------------------------------------------------ host side (no GPU) ---- */
@@ -146,15 +157,16 @@ int rt_camera_init64(rt_camera64 *cam, int width, int height, int spp, int max_d
 
 void rt_opts_default(rt_opts *opts);
 
-/* Number of accumulation chunks for (width, height, spp): depends on nothing else, so the image
- * is the same for every GPU count and launch shape. */
+/* Sample ranges per pixel the scheduler cuts `spp` samples into (jobs of about 32 samples).  Scheduling only: radiance is
+ * accumulated in 64-bit fixed point with integer atomics, so the image depends on neither this number, nor the launch
+ * shape, nor the GPU count. */
 int rt_num_chunks(int width, int height, int spp);
 
 /* Rows rendered by `rank` of `world` under RT_SPLIT_ROWS, ascending.  Returns the count; writes
  * at most `capacity` row indices when `rows` is non-NULL. */
 int rt_partition_rows(int height, int tile_rows, int rank, int world, int32_t *rows, int capacity);
-/* Chunks [*c0, *c1) rendered by `rank` of `world` under RT_SPLIT_SPP. */
-int rt_partition_chunks(int chunks, int rank, int world, int32_t *c0, int32_t *c1);
+/* Samples [*s0, *s1) of every pixel rendered by `rank` of `world` under RT_SPLIT_SPP. */
+int rt_partition_samples(int spp, int rank, int world, int32_t *s0, int32_t *s1);
 
 /* PPM writer, byte-identical with GF main.cu:361-378 (P3, int(256*clamp(x,0,0.999))). */
 int rt_ppm_write(const char *path, const float *rgb, int width, int height);
@@ -189,23 +201,27 @@ int rt_upload_scene64(rt_ctx *ctx, const rt_slot64 *slots, int n);
 int rt_render(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, float *out_rgb, float *render_ms);
 int rt_render64(rt_ctx *ctx, const rt_camera64 *cam, const rt_opts *opts, double *out_rgb, float *render_ms);
 
-/* spp-split building blocks.  rt_render_partials writes, for this rank's chunks c in [c0,c1) and
- * every pixel p, the linear (pre-gamma) chunk sum as 4 floats {r,g,b,0} at
- * partials[((c-c0)*width*height + p)*4]; partials is a DEVICE buffer of (c1-c0)*width*height*4
- * floats.  rt_finalize adds `chunks` such planes in chunk order, scales by 1/spp, applies gamma
- * (GF camera.h:167-171) and writes width*height*3 floats to out_rgb (host or device). */
-int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, float *partials_dev,
-                       float *render_ms);
-int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, int chunks,
-                float *out_rgb, float *finalize_ms);
+/* spp-split building blocks (the north star's "split of samples per pixel across GPUs combined by a reduce of the
+ * accumulation buffer").  rt_render_partials overwrites acc_dev -- a DEVICE buffer of width*height*3 int64 -- with this
+ * rank's radiance sums: acc[3*p + k] = sum over the rank's samples s of round(L_k(p, s) * 2^40) (rt_partition_samples gives
+ * the sample range; RT_SPLIT_NONE: all samples).  Because the sums are integers, buffers of different ranks can be added
+ * in ANY order -- an NCCL sum-reduce of the int64 buffer, or rt_finalize_sum reading peer memory -- and the result is
+ * bit-identical to the single-GPU frame.
+ * rt_finalize / rt_finalize_sum add n_acc such buffers (device pointers; with rt_enable_peer_access they may live on
+ * other GPUs: the cross-GPU sum then happens inside the kernel over NVLink P2P loads), scale by 1/spp, apply gamma
+ * (GF camera.h:167-171, color.h:10-13) and write width*height*3 floats to out_rgb (host or device). */
+int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts, int64_t *acc_dev, float *render_ms);
+int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const int64_t *acc_dev, float *out_rgb, float *finalize_ms);
+int rt_finalize_sum(rt_ctx *ctx, const rt_camera *cam, const int64_t *const *acc_dev, int n_acc, float *out_rgb,
+                    float *finalize_ms);
 
 /* Deterministic primary-ray pass: for every pixel the ray o = cam.center,
  * d = fma(j, dv, fma(i, du, pixel00)) - o goes through the reference's hit_world
  * (GF hittable.h:80-98).  ids: slot index or -1; t: hit distance or +inf.  Host or device. */
 int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t);
 int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double *t);
-/* Same pass through the chosen acceleration structure (RT_ACCEL_LBVH builds the tree on the device
- * on first use); the result is identical to the linear scan's. */
+/* Same pass through the chosen acceleration structure (RT_ACCEL_LBVH builds the tree on the device, RT_ACCEL_GRID the grid
+ * on the host, on first use); the result is identical to the linear scan's. */
 int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t);
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
@@ -218,11 +234,13 @@ int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
  * as degenerate.  All zero when the scene uses the exact scan only. */
 int rt_filter_audit(rt_ctx *ctx, const rt_camera *cam, uint64_t seed, uint64_t n_rays, uint64_t out[5]);
 
-/* Single-process multi-GPU helpers (the CLI's --gpus N): a frame buffer on this context's device that
- * other contexts render into with rt_opts.place_rows, after enabling peer (NVLink P2P) access. */
+/* Single-process multi-GPU helpers (the CLI's --gpus N): a buffer on this context's device -- the frame other contexts
+ * render their rows into with rt_opts.place_rows, or an int64 accumulation buffer of the spp split that device 0 reads in
+ * rt_finalize_sum -- after enabling peer (NVLink P2P) access from the device that touches it. */
 int rt_frame_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr);
 int rt_frame_free(rt_ctx *ctx, void *dev_ptr);
 int rt_frame_read(rt_ctx *ctx, const void *dev_ptr, void *host_ptr, size_t bytes);
+int rt_frame_write(rt_ctx *ctx, void *dev_ptr, const void *host_ptr, size_t bytes);
 int rt_enable_peer_access(rt_ctx *ctx, int peer_device);     /* 0 also when access was already enabled */
 
 #ifdef __cplusplus

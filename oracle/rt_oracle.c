@@ -180,24 +180,30 @@ int orc_scene64(int scene_id, orc_slot64 *slots) {
     return n;
 }
 
-/* ------------------------------------------------------------------ chunk layout ---------- */
-/* Canonical accumulation order: the spp samples of a pixel are split into
- * C contiguous chunks; each chunk is summed sequentially from 0, chunk sums are then added in
- * chunk order.  C depends only on (W, H, spp) so the image does not depend on the GPU count. */
+/* ------------------------------------------------------------------ accumulation ---------- */
+/* Canonical accumulation: every path-sample's radiance is converted to 64-bit fixed point,
+ * round-to-nearest-even(L * 2^40) (saturating; NaN counts as 0), and the pixel value is the INTEGER sum over the samples --
+ * order independent, so the image depends on neither the job partition nor the GPU count.  The frame is
+ * gamma(scale * (REAL)(sum * 2^-40)). */
+int64_t orc_fix(double v) {                       /* v is the float or double radiance; v * 2^40 is exact in either type */
+    if (!(v == v)) return 0;
+    const double x = v * 1099511627776.0;
+    if (x >= 9223372036854775807.0) return INT64_MAX;
+    if (x <= -9223372036854775808.0) return INT64_MIN;
+    return (int64_t)llrint(x);                    /* default rounding mode: to nearest, ties to even (cvt.rni) */
+}
+
+/* Sample ranges per pixel: scheduling only (rt_num_chunks of the product; kept here so the host-logic tests can compare). */
 int orc_num_chunks(int width, int height, int spp) {
-    if (spp <= 8) return spp < 1 ? 1 : spp;
+    if (spp < 1) return 1;
     int64_t npix = (int64_t)width * height;
-    int64_t want = (((int64_t)1 << 22) + npix - 1) / npix;
-    int64_t c = 8 * ((want + 7) / 8);
-    /* at most 32 samples per job (multiples of 8 chunks), partial planes below 8 GiB */
-    int64_t by_spp = 8 * (((int64_t)spp + 255) / 256);
-    int64_t by_mem = 8 * ((((int64_t)1 << 33) / (npix * 16)) / 8);
-    if (by_mem < 8) by_mem = 8;
-    if (by_spp > by_mem) by_spp = by_mem;
-    if (by_spp > c) c = by_spp;
-    int64_t cap = 8 * (int64_t)(spp / 8);
-    if (c > cap) c = cap;
-    if (c > 1024) c = 1024;
+    int64_t c = ((int64_t)spp + 31) / 32;
+    if (npix > 0) {
+        int64_t want = (((int64_t)1 << 20) + npix - 1) / npix;
+        if (want > c) c = want;
+    }
+    if (c > spp) c = spp;
+    if (c > 4096) c = 4096;
     return (int)c;
 }
 
@@ -306,3 +312,13 @@ void orc_render64(const orc_slot64 *slots, int n, const orc_camera64 *cam, uint6
                   int row0, int row1, double *out, uint64_t *segments) {
     render_impl_d(slots, n, cam, seed, row0, row1, out, segments);
 }
+void orc_accumulate(const orc_slot *slots, int n, const orc_camera *cam, uint64_t seed,
+                    int row0, int row1, int s0, int s1, int64_t *acc, uint64_t *segments) {
+    accumulate_impl_f(slots, n, cam, seed, row0, row1, s0, s1, acc, segments);
+}
+void orc_accumulate64(const orc_slot64 *slots, int n, const orc_camera64 *cam, uint64_t seed,
+                      int row0, int row1, int s0, int s1, int64_t *acc, uint64_t *segments) {
+    accumulate_impl_d(slots, n, cam, seed, row0, row1, s0, s1, acc, segments);
+}
+void orc_finalize(const int64_t *acc, uint64_t npix, float scale, float *out) { finalize_impl_f(acc, (size_t)npix, scale, out); }
+void orc_finalize64(const int64_t *acc, uint64_t npix, double scale, double *out) { finalize_impl_d(acc, (size_t)npix, scale, out); }

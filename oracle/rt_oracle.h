@@ -77,8 +77,17 @@ int  orc_hit_world(const orc_slot *slots, int n, const float o[3], const float d
 /* deterministic primary pass: ray through every pixel centre from cam.center */
 void orc_primary(const orc_slot *slots, int n, const orc_camera *cam, int32_t *ids, float *t);
 
-/* chunk layout of the canonical accumulation order */
+/* sample ranges per pixel of the product's scheduler (rt_num_chunks; scheduling only, the image does not depend on it) */
 int  orc_num_chunks(int width, int height, int spp);
+
+/* Canonical accumulation: fix40(v) = round-to-nearest-even(v * 2^40) as int64 (saturating, NaN -> 0);
+ * a pixel's accumulators are the INTEGER sums of fix40 over its samples.  orc_accumulate ADDS the samples [s0,s1) of rows
+ * [row0,row1) to acc[(row1-row0)*width*3]; orc_finalize turns accumulators into gamma-encoded floats
+ * (GF camera.h:167-171).  orc_render = zero, accumulate all samples, finalize. */
+int64_t orc_fix(double v);
+void orc_accumulate(const orc_slot *slots, int n, const orc_camera *cam, uint64_t seed,
+                    int row0, int row1, int s0, int s1, int64_t *acc, uint64_t *segments);
+void orc_finalize(const int64_t *acc, uint64_t npix, float scale, float *out);
 
 /* One path-sample: linear radiance of (pixel, sample) under the Philox sampling spec of
  * DESIGN.md.  `segments` (optional) is incremented once per hit_world call. */
@@ -127,6 +136,9 @@ void orc_sample64(const orc_slot64 *slots, int n, const orc_camera64 *cam, uint6
                   int i, int j, int sample, double rgb[3], uint64_t *segments);
 void orc_render64(const orc_slot64 *slots, int n, const orc_camera64 *cam, uint64_t seed,
                   int row0, int row1, double *out, uint64_t *segments);
+void orc_accumulate64(const orc_slot64 *slots, int n, const orc_camera64 *cam, uint64_t seed,
+                      int row0, int row1, int s0, int s1, int64_t *acc, uint64_t *segments);
+void orc_finalize64(const int64_t *acc, uint64_t npix, double scale, double *out);
 
 #ifdef __cplusplus
 }

@@ -6,9 +6,9 @@ The product is the C-ABI library ``librt_b200.so`` (include/rt_b200.h) and the d
 :mod:`raytracingincuda_b200.api` raises if the library has not been built.
 """
 from .api import (Camera, Camera64, Opts, Renderer, RtError, Slot, Slot64, SLOT_DTYPE, SLOT64_DTYPE, Stats,
-                  camera, lib, load_scene, num_chunks, partition_chunks, partition_rows, ppm_quantise, ppm_write, save_scene, scene,
+                  camera, lib, load_scene, num_chunks, partition_samples, partition_rows, ppm_quantise, ppm_write, save_scene, scene,
                   scene_scaled)
 
 __all__ = ["Camera", "Camera64", "Opts", "Renderer", "RtError", "Slot", "Slot64", "SLOT_DTYPE", "SLOT64_DTYPE",
-           "Stats", "camera", "lib", "load_scene", "num_chunks", "partition_chunks", "partition_rows", "ppm_quantise",
+           "Stats", "camera", "lib", "load_scene", "num_chunks", "partition_samples", "partition_rows", "ppm_quantise",
            "ppm_write", "save_scene", "scene", "scene_scaled"]

@@ -56,7 +56,9 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("node_visits", C.c_uint64), ("render_ms", C.c_float), ("trace_ms", C.c_float),
                 ("launches", C.c_int32), ("chunks", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
-                ("regs", C.c_int32), ("smem_bytes", C.c_int32), ("binned_segments", C.c_uint64)]
+                ("regs", C.c_int32), ("smem_bytes", C.c_int32), ("binned_segments", C.c_uint64),
+                ("filter_tests", C.c_uint64), ("bvh_build_ms", C.c_float), ("grid_build_ms", C.c_float),
+                ("accel_used", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)
@@ -71,7 +73,7 @@ SYMBOLS = {
     "rt_opts_default": (None, [_P]),
     "rt_num_chunks": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rt_partition_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
-    "rt_partition_chunks": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rt_partition_samples": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
     "rt_ppm_write": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_int]),
     "rt_ppm_write64": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_int]),
     "rt_ppm_quantise": (C.c_int, [_P, C.c_size_t, _P]),
@@ -84,7 +86,8 @@ SYMBOLS = {
     "rt_render": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
     "rt_render64": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
     "rt_render_partials": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
-    "rt_finalize": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(C.c_float)]),
+    "rt_finalize": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_float)]),
+    "rt_finalize_sum": (C.c_int, [_P, _P, _P, C.c_int, _P, C.POINTER(C.c_float)]),
     "rt_primary_hits": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
@@ -95,6 +98,7 @@ SYMBOLS = {
     "rt_frame_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "rt_frame_free": (C.c_int, [_P, _P]),
     "rt_frame_read": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "rt_frame_write": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rt_enable_peer_access": (C.c_int, [_P, C.c_int]),
 }
 
@@ -179,10 +183,11 @@ def partition_rows(height, tile_rows, rank, world):
     return rows
 
 
-def partition_chunks(chunks, rank, world):
-    c0, c1 = C.c_int32(), C.c_int32()
-    _ck(lib().rt_partition_chunks(chunks, rank, world, C.byref(c0), C.byref(c1)), "rt_partition_chunks")
-    return c0.value, c1.value
+def partition_samples(spp, rank, world):
+    """Samples [s0, s1) of every pixel that `rank` of `world` renders under SPLIT_SPP."""
+    s0, s1 = C.c_int32(), C.c_int32()
+    _ck(lib().rt_partition_samples(spp, rank, world, C.byref(s0), C.byref(s1)), "rt_partition_samples")
+    return s0.value, s1.value
 
 
 def ppm_write(path, rgb):
@@ -202,14 +207,15 @@ def ppm_quantise(rgb):
     return out
 
 
-ACCEL_LINEAR, ACCEL_LBVH, ACCEL_AUTO = 0, 1, 2
-ACCEL_GRID = 4          # experimental (csrc/rt_grid.cuh): refused unless RT_ENABLE_GRID=1 is in the environment
+ACCEL_LINEAR, ACCEL_LBVH, ACCEL_AUTO, ACCEL_GRID = 0, 1, 2, 4
+ACCEL_NAMES = {ACCEL_LINEAR: "linear", ACCEL_LBVH: "lbvh", ACCEL_AUTO: "auto", ACCEL_GRID: "grid"}
 KERNEL_MEGA, KERNEL_WAVEFRONT = 0, 1
 PBINS_AUTO, PBINS_OFF, PBINS_ON = 0, 1, 2
 
 
-def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_LINEAR,
+def make_opts(seed=1227, split=SPLIT_NONE, rank=0, world=1, tile_rows=1, threads=8, accel=ACCEL_AUTO,
               kernel=KERNEL_MEGA, primary_bins=PBINS_AUTO):
+    """rt_opts; the defaults are rt_opts_default's (accel AUTO: the fastest structure, same image bit for bit)."""
     o = Opts()
     lib().rt_opts_default(C.byref(o))
     o.seed, o.split, o.rank, o.world, o.tile_rows, o.threads = seed, split, rank, world, tile_rows, threads
@@ -287,19 +293,27 @@ class Renderer:
         self.last_ms = ms.value
         return out
 
-    def render_partials(self, cam, opts, partials_dev):
+    def render_partials(self, cam, opts, acc_dev):
+        """rt_render_partials: overwrite the DEVICE int64 buffer `acc_dev` (height*width*3) with this rank's fixed-point
+        radiance sums (opts.split SPLIT_SPP: its share of the samples; SPLIT_NONE: all of them)."""
         ms = C.c_float(0)
-        _ck(lib().rt_render_partials(self._ctx, C.byref(cam), C.byref(opts), _ptr(partials_dev), C.byref(ms)),
+        _ck(lib().rt_render_partials(self._ctx, C.byref(cam), C.byref(opts), _ptr(acc_dev), C.byref(ms)),
             "rt_render_partials")
         self.last_ms = ms.value
         return ms.value
 
-    def finalize(self, cam, partials_dev, chunks, out=None):
+    def finalize(self, cam, acc_dev, out=None):
+        """rt_finalize / rt_finalize_sum: one accumulation buffer or a list of them (device pointers, possibly on peer
+        GPUs) -> gamma-encoded frame."""
         if out is None:
             out = np.empty((cam.height, cam.width, 3), dtype=np.float32)
         ms = C.c_float(0)
-        _ck(lib().rt_finalize(self._ctx, C.byref(cam), _ptr(partials_dev), chunks, _ptr(out), C.byref(ms)),
-            "rt_finalize")
+        if isinstance(acc_dev, (list, tuple)):
+            ptrs = (C.c_void_p * len(acc_dev))(*[_ptr(a) for a in acc_dev])
+            _ck(lib().rt_finalize_sum(self._ctx, C.byref(cam), ptrs, len(acc_dev), _ptr(out), C.byref(ms)), "rt_finalize_sum")
+        else:
+            _ck(lib().rt_finalize(self._ctx, C.byref(cam), _ptr(acc_dev), _ptr(out), C.byref(ms)), "rt_finalize")
+        self.last_finalize_ms = ms.value
         return out
 
     def primary_hits(self, cam, accel=ACCEL_LINEAR):

@@ -70,6 +70,32 @@ __device__ __forceinline__ T dot3(const Vec3<T> &u, const Vec3<T> &v) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Order-independent accumulation.  The radiance of one path-sample is converted to 64-bit fixed
+// point, round(L * 2^40), and ADDED with an integer atomic to the pixel's three accumulators.  Integer addition is
+// associative, so the pixel sum -- and with it the image -- does not depend on which lane, CTA, job partition or GPU traced
+// which sample, nor on the order in which they finished: the canonical image is
+//     gamma( scale * float( sum_s fix40(L(p, s)) * 2^-40 ) )
+// with no partial planes and no ordered reduction.  L <= 1 for the reference's materials (albedo <= 1, sky <= 1), so the
+// sum stays below spp * 2^40 (exact in int64 up to 2^23 samples); multiplying by 2^40 is exact in float and double, the
+// conversion rounds to nearest-even and saturates, and a NaN sample counts as 0.
+constexpr int FIX_SHIFT = 40;
+__device__ __forceinline__ long long fix_of(float v) {
+    return (v == v) ? __float2ll_rn(__fmul_rn(v, 1099511627776.0f)) : 0ll;
+}
+__device__ __forceinline__ long long fix_of(double v) {
+    return (v == v) ? __double2ll_rn(__dmul_rn(v, 1099511627776.0)) : 0ll;
+}
+// acc[3 * pixel + k] += fix40(c_k); black samples add nothing
+template <typename T>
+__device__ __forceinline__ void accumulate(long long *__restrict__ acc, uint32_t local_pixel, T cr, T cg, T cb) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(acc) + 3ull * local_pixel;
+    const long long fr = fix_of(cr), fg = fix_of(cg), fb = fix_of(cb);
+    if (fr) atomicAdd(a, (unsigned long long)fr);
+    if (fg) atomicAdd(a + 1, (unsigned long long)fg);
+    if (fb) atomicAdd(a + 2, (unsigned long long)fb);
+}
+
+// ------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (pixel, sample, dimension, block), key = seed.
 // The ten round keys depend on the seed only: the host expands them once (philox_keys) and the
 // kernels read them from the parameter constant bank, so a block is 20 IMAD.WIDE + 20 LOP3.
@@ -225,6 +251,10 @@ constexpr int CAND_CAP = 32;       // exact scan: a list of 32 uint16 slots per 
 
 template <typename T> struct Hit { T t; int id; };
 
+// Work a lane actually executed in the scan (for the executed-FP32 roofline, bench.py): filter tests (7 FMA each) and exact
+// sphere tests (the reference's 12 FP32 instructions each, plus sqrt/div on the few that pass).
+struct ScanCount { unsigned int filt, exact; };
+
 struct ScanGeom {
     uint32_t addr;        // shared-space byte address of geom[0]
     int blocks;           // n / 32 full blocks
@@ -323,7 +353,7 @@ __device__ __forceinline__ void push_candidates(uint32_t m, int base, unsigned s
 
 template <typename T>
 __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
-                                                    unsigned short *cand, int stride) {
+                                                    unsigned short *cand, int stride, ScanCount &cnt) {
     using N = Num<T>;
     constexpr uint32_t REC = sizeof(typename N::vec4);
     const T a = dot3(d, d);                                     // GF hittable.h:42
@@ -364,6 +394,7 @@ __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, co
     Hit<T> hit;
     hit.t = N::inf();
     hit.id = -1;
+    cnt.exact += (unsigned)(32 * g.blocks + 8 * g.tail_groups) + (unsigned)(count <= CAND_CAP ? count : n);
     if (count <= CAND_CAP) {
 #pragma unroll 1
         for (int k = 0; k < count; ++k) {
@@ -482,7 +513,7 @@ __device__ __forceinline__ void filter_pair(const float4 q, const PairRay &r, ui
 // (DESIGN.md section 6), and the candidates are resolved in double.
 template <typename T>
 __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
-                                                     unsigned short *cand, int stride) {
+                                                     unsigned short *cand, int stride, ScanCount &cnt) {
     using N = Num<T>;
     constexpr unsigned FULLMASK = 0xffffffffu;
     Vec3<float> of, df;
@@ -567,10 +598,12 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
                 const int k = __ffs(w) - 1;
                 w &= w - 1u;
                 resolve_slot<T>(g.addr, base + k, o, d, a, hit);
+                ++cnt.exact;
             }
         }
         __syncwarp();                                                // words are rewritten by the next chunk / scan
     }
+    cnt.filt += 2u * (unsigned)g.half_pad;                           // every lane: its half of the records x two rays
     if (sane) {
 #pragma unroll 1
         for (int k = 0; k < g.n_far; ++k) {
@@ -578,6 +611,7 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(g.far_addr + (uint32_t)k * 4u));
             resolve_slot<T>(g.addr, id, o, d, a, hit);
         }
+        cnt.exact += (unsigned)g.n_far;
     } else {
         // Degenerate ray (inf / denormal scale): the reference's loop, slot by slot.  A ray with a NaN component needs no loop:
         // it poisons h or |oc|^2 of every slot, every discriminant is NaN, and GF hittable.h:47-55 accepts nothing (all its
@@ -585,7 +619,7 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
         // normal (p - c) * (1/0); in scene 1 about one segment in 10^4 is one, and its 488-slot loop stalled the whole warp
         // (1.4 % of the stall samples before this shortcut).
         const bool nan_ray = !(o.x == o.x && o.y == o.y && o.z == o.z && d.x == d.x && d.y == d.y && d.z == d.z);
-        if (!nan_ray) hit = rescan_in_order<T>(g.addr, n, o, d, a);
+        if (!nan_ray) { hit = rescan_in_order<T>(g.addr, n, o, d, a); cnt.exact += (unsigned)n; }
     }
     return hit;
 }
@@ -593,9 +627,15 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
 // hit_world (GF hittable.h:80-98).  All 32 lanes of the warp must call it together.
 template <typename T>
 __device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
+                                              unsigned short *cand, int stride, ScanCount &cnt) {
+    if (g.filter_ok) return closest_hit_paired<T>(g, n, o, d, cand, stride, cnt);
+    return closest_hit_exact<T>(g, n, o, d, cand, stride, cnt);
+}
+template <typename T>
+__device__ __forceinline__ Hit<T> closest_hit(const ScanGeom &g, int n, const Vec3<T> &o, const Vec3<T> &d,
                                               unsigned short *cand, int stride) {
-    if (g.filter_ok) return closest_hit_paired<T>(g, n, o, d, cand, stride);
-    return closest_hit_exact<T>(g, n, o, d, cand, stride);
+    ScanCount cnt{0u, 0u};
+    return closest_hit<T>(g, n, o, d, cand, stride, cnt);
 }
 
 }  // namespace rt

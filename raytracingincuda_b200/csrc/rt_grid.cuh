@@ -91,11 +91,16 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
         // Inflation of THIS step: a sphere whose root lies in the current cell is at most t_far |d| + 2 h + delta away from
         // the origin (t_far: where the ray leaves the cell or the walk ends).  With the one inflation per ray of the first
         // version (evaluated at the far corner of the grid) every step of the 99 860-slot scene looked at two rings of cells.
-        const float t_far = fminf(fminf(tu, tw), t1);
-        const float Ds = (t_far * length) * 1.0001f + (2.0f * g.h + delta);
-        const float rs = sqrt_approx(BVH_KEPS * (Ds * Ds) + g.rmin * g.rmin) * (1.0f + 2e-7f);
-        const float ds = ((rs - g.rmin) * 1.001f + 1e-7f) + 4.8e-7f * (omax + Ds);
-        const int k = ds <= half_pad ? 0 : min((int)fminf(ceilf((ds - half_pad) / g.h), 8192.0f) + 1, k_global);
+        // Rays whose inflation at the far corner of the field already stays inside the padding (k_global == 0: every ray of a
+        // compact scene) skip this.
+        int k = 0;
+        if (k_global > 0) {
+            const float t_far = fminf(fminf(tu, tw), t1);
+            const float Ds = (t_far * length) * 1.0001f + (2.0f * g.h + delta);
+            const float rs = sqrt_approx(BVH_KEPS * (Ds * Ds) + g.rmin * g.rmin) * (1.0f + 2e-7f);
+            const float ds = ((rs - g.rmin) * 1.001f + 1e-7f) + 4.8e-7f * (omax + Ds);
+            k = ds <= half_pad ? 0 : min((int)fminf(ceilf((ds - half_pad) / g.h), 8192.0f) + 1, k_global);
+        }
         const int cu = min(max(iu, 0), g.nu - 1), cw = min(max(iw, 0), g.nw - 1);
         for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
             for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {

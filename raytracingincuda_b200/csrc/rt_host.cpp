@@ -312,27 +312,24 @@ void rt_opts_default(rt_opts *opts) {
     opts->rank = 0;
     opts->world = 1;
     opts->tile_rows = 1;
-    opts->accel = RT_ACCEL_LINEAR;
+    opts->accel = RT_ACCEL_AUTO;
     opts->threads = 8;
     opts->kernel = RT_KERNEL_MEGA;
 }
 
-// Chunk layout of the canonical accumulation order.  At least 2^22 jobs
-// (pixel x chunk) when spp allows, a multiple of 8 so that 1/2/4/8 GPUs split chunks evenly.
+// Sample ranges per pixel (scheduling only, see the header).  Jobs of about 32 samples: a launch ends when its last job
+// ends, and long jobs leave the machine draining (125-sample jobs cost a fixed 27 ms per launch at config 4, 32-sample jobs
+// 10 ms); small frames get more, shorter jobs so that there are at least 2^20 of them when spp allows.
 int rt_num_chunks(int width, int height, int spp) {
-    if (spp <= 8) return spp < 1 ? 1 : spp;
+    if (spp < 1) return 1;
     const int64_t npix = static_cast<int64_t>(width) * height;
-    const int64_t want = ((int64_t(1) << 22) + npix - 1) / npix;
-    int64_t c = 8 * ((want + 7) / 8);
-    // Jobs of at most 32 samples: the kernel ends when its last job ends, and with 125 samples per job (config 4 with 8 chunks)
-    // that drain was a fixed 27 ms per launch -- 6 % of the step on 8 GPUs.  Bounded so that the partial planes stay below 8 GiB.
-    const int64_t by_spp = 8 * ((static_cast<int64_t>(spp) + 255) / 256);
-    int64_t by_mem = 8 * (((int64_t(1) << 33) / (npix * 16)) / 8);
-    if (by_mem < 8) by_mem = 8;
-    if ((by_spp < by_mem ? by_spp : by_mem) > c) c = by_spp < by_mem ? by_spp : by_mem;
-    const int64_t cap = 8 * static_cast<int64_t>(spp / 8);
-    if (c > cap) c = cap;
-    if (c > 1024) c = 1024;
+    int64_t c = (static_cast<int64_t>(spp) + 31) / 32;
+    if (npix > 0) {
+        const int64_t want = ((int64_t(1) << 20) + npix - 1) / npix;
+        if (want > c) c = want;
+    }
+    if (c > spp) c = spp;
+    if (c > 4096) c = 4096;
     return static_cast<int>(c);
 }
 
@@ -347,10 +344,10 @@ int rt_partition_rows(int height, int tile_rows, int rank, int world, int32_t *r
     return n;
 }
 
-int rt_partition_chunks(int chunks, int rank, int world, int32_t *c0, int32_t *c1) {
-    if (chunks <= 0 || world <= 0 || rank < 0 || rank >= world || !c0 || !c1) return RT_EINVAL;
-    *c0 = static_cast<int32_t>(static_cast<int64_t>(chunks) * rank / world);
-    *c1 = static_cast<int32_t>(static_cast<int64_t>(chunks) * (rank + 1) / world);
+int rt_partition_samples(int spp, int rank, int world, int32_t *s0, int32_t *s1) {
+    if (spp <= 0 || world <= 0 || rank < 0 || rank >= world || !s0 || !s1) return RT_EINVAL;
+    *s0 = static_cast<int32_t>(static_cast<int64_t>(spp) * rank / world);
+    *s1 = static_cast<int32_t>(static_cast<int64_t>(spp) * (rank + 1) / world);
     return RT_OK;
 }
 

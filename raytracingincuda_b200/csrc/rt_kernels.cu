@@ -9,7 +9,7 @@
 //   trace_kernel_pb  (rt_primary_bins.cuh, the default) the same persistent tracer with the camera rays resolved against
 //                    per-tile candidate lists that bin_kernel / bin_kernel_bvh build on the device before the frame;
 //                    scattered rays go through the shared-memory scan or the LBVH.  Same image, bit for bit.
-//   finalize_kernel  sums the chunk partials in chunk order, scales, gamma-encodes and writes
+//   finalize_kernel  adds the fixed-point accumulators (of one or several GPUs), scales, gamma-encodes and writes
 //                    the frame with 16-byte vector stores (GF camera.h:167-171, color.h:10-13).
 //   primary_kernel   deterministic primary-ray (slot id, t) pass through the same closest-hit
 //                    routine (parity probe for GF hittable.h:80-98).
@@ -23,6 +23,7 @@
 #include <cstring>
 #include <new>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <vector>
 
@@ -45,21 +46,36 @@ template <typename T> struct DevCamera {
     T scale;
 };
 
+// Job = (pixel, sample range).  The image does not depend on how the samples are cut into jobs (integer accumulation,
+// rt_device.cuh), so the cut is a pure scheduling choice (JobPlan, plan_jobs below): pixels are handed out in BANDS of rows
+// small enough that a band's accumulators stay in L2 while its jobs run, bottom band first; inside a band chunk-major.  All
+// bands but the last (the top rows of the frame) use `chunks[0]` sample ranges per pixel, the last band four times as many:
+// a launch ends when its last job ends, so the jobs that run while the machine drains are short ones on sky pixels.
+struct JobPlan {
+    unsigned long long pix_local;      // pixels rendered by this launch
+    unsigned long long total_jobs;
+    unsigned long long jobs_a;         // jobs of region A (all bands but the last); region B follows
+    unsigned long long band_jobs;      // band_pix * chunks[0]
+    unsigned long long rp_b;           // first reversed pixel of region B = (bands - 1) * band_pix
+    unsigned long long magic_band_jobs, magic_width;      // floor(2^64 / d) + 1 (0 encodes d == 1)
+    unsigned long long magic_pix[2];                      // ... for band_pix / last_pix
+    unsigned int band_pix, last_pix;   // pixels per full band / in the last band
+    int chunks[2];                     // sample ranges per pixel in region A / B
+    int spp_q[2], spp_r[2];            // s_count / chunks and s_count % chunks
+    int s_begin, s_count;              // this launch traces samples [s_begin, s_begin + s_count) of every pixel
+};
+
 template <typename T> struct TraceArgs {
     DevCamera<T> cam;
     SceneBlob scene;
     PhiloxKeys keys;                   // Philox round keys of the seed
-    int spp, max_depth;
+    int max_depth;
     int width;
     int tile_rows, rank, world;        // local row -> global row (world == 1: identity)
-    int chunks, c_begin;               // C and the first chunk of this launch
-    int spp_q, spp_r;                  // spp / C and spp % C: first sample of chunk c = c*spp_q + c*spp_r / C (32-bit, C <= 1024)
-    unsigned long long pix_local;      // pixels rendered by this launch
-    unsigned long long total_jobs;     // (c_end - c_begin) * pix_local
-    unsigned long long magic_pix;      // floor(2^64 / pix_local) + 1: job / pix_local == umul64hi(job, magic_pix)
-    unsigned long long magic_width;    // floor(2^64 / width) + 1
-    typename Num<T>::vec4 *partial;    // [job]
-    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes, [4] sphere tests, [5] binned camera segments
+    JobPlan plan;
+    long long *acc;                    // [pix_local][3] fixed-point radiance sums (rt_device.cuh: accumulate)
+    unsigned long long *queue;         // [0] job cursor, [1] segments, [2] paths, [3] BVH nodes / grid cells, [4] exact sphere tests,
+                                       // [5] binned camera segments, [6] filter tests
     BvhView bvh;                       // RT_ACCEL_LBVH only
     int bvh_steps;                     // at most this many node visits per loop turn ...
     int bvh_min_active;                // ... and the round ends once fewer lanes than this are still traversing
@@ -236,12 +252,6 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
     return true;
 }
 
-// floor(c * spp / C) without the 64-bit division (it was 1.7 % of the stall samples at config 2's 12 samples per job)
-template <typename T>
-__device__ __forceinline__ int first_sample(const TraceArgs<T> &A, int c) {
-    return c * A.spp_q + (int)((unsigned)(c * A.spp_r) / (unsigned)A.chunks);
-}
-
 template <typename T>
 __device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) {
     if (A.world == 1) return local_row;
@@ -249,29 +259,40 @@ __device__ __forceinline__ int global_row(const TraceArgs<T> &A, int local_row) 
     return (tile * A.world + A.rank) * A.tile_rows + within;
 }
 
-// Job = (pixel, chunk), numbered chunk-major.  decode_job turns a queue index into the place of the job's sum in the partial
-// planes, the pixel and the sample range.  The pixels of a chunk are handed out last to first, i.e. bottom rows first: the
-// kernel ends when the last job ends, and a sky pixel's job is a fraction of an average one, so the jobs that run while the
-// machine drains should be the top rows (sky in the reference's scenes).
+// decode_job turns a queue index into the pixel and the sample range (JobPlan above).  Exact divisions by multiply-high:
+// the host checks that every dividend * divisor stays below 2^63.
 struct JobInfo {
-    unsigned long long store;          // index of the job's float4 in the partial planes
     int pi, pj, sample, sample_end;
-    uint32_t pixel;
+    uint32_t pixel;                    // global pixel index (Philox counter word 0)
+    uint32_t local;                    // index of the pixel in this launch's accumulators
 };
+__device__ __forceinline__ unsigned long long div_magic(unsigned long long x, unsigned long long magic) {
+    return magic ? __umul64hi(x, magic) : x;
+}
 template <typename T>
 __device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned long long job) {
+    const JobPlan &P = A.plan;
     JobInfo J;
-    // exact divisions by multiply-high (job * pix_local and lp * width stay far below 2^64)
-    const unsigned long long cl = A.magic_pix ? __umul64hi(job, A.magic_pix) : job;            // magic 0: divisor 1
-    const unsigned long long lp = A.pix_local - 1ull - (job - cl * A.pix_local);
-    J.store = cl * A.pix_local + lp;
-    const int c = A.c_begin + (int)cl;
-    const int lr = (int)(A.magic_width ? __umul64hi(lp, A.magic_width) : lp);
+    const int reg = job >= P.jobs_a;                                   // region B: the last band, finer sample ranges
+    unsigned long long r, rp0;
+    if (reg) { r = job - P.jobs_a; rp0 = P.rp_b; }
+    else {
+        const unsigned long long band = div_magic(job, P.magic_band_jobs);
+        r = job - band * P.band_jobs;
+        rp0 = band * P.band_pix;
+    }
+    const unsigned long long bp = reg ? P.last_pix : P.band_pix;
+    const unsigned long long cl = div_magic(r, P.magic_pix[reg]);
+    const unsigned long long lp = P.pix_local - 1ull - (rp0 + (r - cl * bp));   // bands are counted from the bottom of the frame
+    const int lr = (int)div_magic(lp, P.magic_width);
     J.pi = (int)(lp - (unsigned long long)lr * A.width);
     J.pj = global_row(A, lr);
     J.pixel = (uint32_t)J.pj * (uint32_t)A.width + (uint32_t)J.pi;
-    J.sample = first_sample(A, c);
-    J.sample_end = first_sample(A, c + 1);
+    J.local = (uint32_t)lp;
+    // floor(c * S / C) without a 64-bit division
+    const int c = (int)cl, C = P.chunks[reg], q = P.spp_q[reg], rem = P.spp_r[reg];
+    J.sample = P.s_begin + c * q + (int)((unsigned)(c * rem) / (unsigned)C);
+    J.sample_end = P.s_begin + (c + 1) * q + (int)((unsigned)((c + 1) * rem) / (unsigned)C);
     return J;
 }
 
@@ -283,6 +304,18 @@ __device__ __forceinline__ unsigned long long claim_job(const TraceArgs<T> &A, i
     if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)__popc(want));
     base = __shfl_sync(FULL, base, leader);
     return base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+}
+
+// per-warp reduction of the lanes' work counters into the queue words 1..6
+__device__ __forceinline__ void flush_counters(unsigned long long *queue, int lane, unsigned n_seg, unsigned n_path, unsigned n_nodes,
+                                               unsigned n_exact, unsigned n_binned, unsigned n_filt) {
+    unsigned long long v[6] = {n_seg, n_path, n_nodes, n_exact, n_binned, n_filt};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], off);
+        if (lane == 0 && v[q]) atomicAdd(queue + 1 + q, v[q]);
+    }
 }
 
 template <typename T, int ACCEL>
@@ -322,25 +355,23 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     Hit<T> hit;                         // pending hit of the previous turn's scan
     hit.t = N::inf();
     hit.id = -1;
-    T acc_r = T(0), acc_g = T(0), acc_b = T(0);
     int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
-    uint32_t pixel = 0;
-    unsigned long long job = 0;
+    uint32_t pixel = 0, local = 0;
     unsigned int n_seg = 0, n_path = 0;
+    ScanCount cnt{0u, 0u};
 
-    // a path ended with radiance (cr,cg,cb): accumulate (GF camera.h:160), move to the next sample
-    // of the job or hand the job's sum back
+    // a path ended with radiance (cr,cg,cb): add it to the pixel's accumulators (GF camera.h:160), move to the next
+    // sample of the job or ask for the next job
     auto end_path = [&](T cr, T cg, T cb) {
-        acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);
+        accumulate<T>(A.acc, local, cr, cg, cb);
         ++n_path;
-        if (++sample == sample_end) {
-            typename N::vec4 v;
-            v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
-            A.partial[job] = v;
-            state = NEED_JOB;
-        } else {
-            fresh = true;
-        }
+        if (++sample == sample_end) state = NEED_JOB;
+        else fresh = true;
+    };
+    auto end_black = [&]() {
+        ++n_path;
+        if (++sample == sample_end) state = NEED_JOB;
+        else fresh = true;
     };
 
     for (;;) {
@@ -349,12 +380,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         if (want) {
             const unsigned long long claimed = claim_job(A, lane, want);
             if (state == NEED_JOB) {
-                if (claimed < A.total_jobs) {
+                if (claimed < A.plan.total_jobs) {
                     const JobInfo J = decode_job(A, claimed);
-                    job = J.store;
-                    pi = J.pi; pj = J.pj; pixel = J.pixel;
+                    pi = J.pi; pj = J.pj; pixel = J.pixel; local = J.local;
                     sample = J.sample; sample_end = J.sample_end;
-                    acc_r = acc_g = acc_b = T(0);
                     state = ACTIVE;
                     fresh = true;
                 } else {
@@ -377,7 +406,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             // shade the hit found by the previous scan
             const bool alive = scatter(sc, hit, ph, ps);
             if (!alive || ++depth >= A.max_depth) {                       // GF camera.h:117 / :84,127 -> black
-                end_path(T(0), T(0), T(0));
+                end_black();
                 if (state == ACTIVE) {                                    // rare: regenerate right away
                     ph.open(A.keys, pixel, (uint32_t)sample, 0u);
                     ph.block(0);
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
             if (landed) hit = tv.hit;
         } else {
             // ---- closest hit over all slots (all 32 lanes, uniform trip count) ----
-            hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+            hit = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK, cnt);
             landed = (state == ACTIVE);
         }
 
@@ -425,26 +454,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
         }
     }
 
-    // ---- work counters (for the roofline: segments x slots x 18 FLOP) ----
-    unsigned long long seg = n_seg, pth = n_path;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        seg += __shfl_xor_sync(FULL, seg, off);
-        pth += __shfl_xor_sync(FULL, pth, off);
-    }
-    if (lane == 0) {
-        atomicAdd(A.queue + 1, seg);
-        atomicAdd(A.queue + 2, pth);
-    }
-    if (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT) {
-        unsigned long long nod = n_nodes, tst = n_tests;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            nod += __shfl_xor_sync(FULL, nod, off);
-            tst += __shfl_xor_sync(FULL, tst, off);
-        }
-        if (lane == 0) { atomicAdd(A.queue + 3, nod); atomicAdd(A.queue + 4, tst); }
-    }
+    // ---- work counters (reference-equivalent work: segments x slots; executed work: filter + exact tests, node visits) ----
+    flush_counters(A.queue, lane, n_seg, n_path, n_nodes, n_tests + cnt.exact, 0u, cnt.filt);
 }
 
 }  // namespace rt
@@ -455,8 +466,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
 namespace rt {
 
 // ------------------------------------------------------------------------------------------
-// out[p] = gamma(scale * sum_c partial[c][p]); 4 pixels per thread, 16-byte stores.
+// out[p] = gamma(scale * float(sum_g acc_g[p] * 2^-40)); 4 pixels per thread, 16-byte loads and stores.
+// `src` lists the accumulation buffers to add: one for a whole-frame or rows render, one per GPU for the spp split --
+// there the pointers are the PEERS' buffers (NVLink P2P loads, rt_enable_peer_access), so the cross-GPU reduction, the
+// scale, the gamma and the store are one kernel; integer sums make the result independent of the order.
 struct RowPlacement { int width, tile_rows, rank, world; };    // world == 1: rows stay where they are
+constexpr int ACC_SOURCES_MAX = 16;
+struct AccSources { const long long *p[ACC_SOURCES_MAX]; int n; };
 
 __device__ __forceinline__ unsigned long long placed_pixel(const RowPlacement &rp, unsigned long long p) {
     if (rp.world == 1) return p;
@@ -465,30 +481,40 @@ __device__ __forceinline__ unsigned long long placed_pixel(const RowPlacement &r
     return (unsigned long long)((tile * rp.world + rp.rank) * rp.tile_rows + within) * rp.width + col;
 }
 
+template <typename T> __device__ __forceinline__ T unfix(long long v);
+template <> __device__ __forceinline__ float unfix<float>(long long v) {
+    return __double2float_rn(__dmul_rn(__ll2double_rn(v), 9.094947017729282e-13));       // 2^-40
+}
+template <> __device__ __forceinline__ double unfix<double>(long long v) { return __dmul_rn(__ll2double_rn(v), 9.094947017729282e-13); }
+
 template <typename T>
-__global__ void __launch_bounds__(256) finalize_kernel(const typename Num<T>::vec4 *__restrict__ partial, int chunks,
-                                                       unsigned long long pix, T scale, T *__restrict__ out,
-                                                       const RowPlacement rp) {
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ AccSources src, unsigned long long pix, T scale,
+                                                       T *__restrict__ out, const RowPlacement rp) {
     using N = Num<T>;
     const unsigned long long quad = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long p0 = quad * 4ull;
     if (p0 >= pix) return;
     T v[12];
     const int cnt = (pix - p0) < 4ull ? (int)(pix - p0) : 4;
+    long long sum[12];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        T r = T(0), g = T(0), b = T(0);
-        if (k < cnt) {
-            for (int c = 0; c < chunks; ++c) {
-                const typename N::vec4 q = partial[(unsigned long long)c * pix + p0 + k];
-                r = N::add(r, q.x); g = N::add(g, q.y); b = N::add(b, q.z);
+    for (int k = 0; k < 12; ++k) sum[k] = 0;
+    for (int g = 0; g < src.n; ++g) {
+        const long long *a = src.p[g] + 3ull * p0;                      // 96-byte groups: 16-byte aligned
+        if (cnt == 4) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const longlong2 q = *reinterpret_cast<const longlong2 *>(a + 2 * k);
+                sum[2 * k] += q.x; sum[2 * k + 1] += q.y;
             }
-            r = N::mul(r, scale); g = N::mul(g, scale); b = N::mul(b, scale);          // GF camera.h:167
-            r = r > T(0) ? N::sqrt(r) : T(0);                                          // GF color.h:10-13
-            g = g > T(0) ? N::sqrt(g) : T(0);
-            b = b > T(0) ? N::sqrt(b) : T(0);
+        } else {
+            for (int k = 0; k < 3 * cnt; ++k) sum[k] += a[k];
         }
-        v[3 * k] = r; v[3 * k + 1] = g; v[3 * k + 2] = b;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        T c = N::mul(unfix<T>(sum[k]), scale);                          // GF camera.h:167
+        v[k] = c > T(0) ? N::sqrt(c) : T(0);                            // GF color.h:10-13
     }
     // row placement (multi-GPU direct stores into the full frame): a group of 4 pixels stays inside one
     // row when the width is a multiple of 4, otherwise fall back to per-pixel stores
@@ -658,9 +684,9 @@ struct rt_ctx {
     void *scene_dev = nullptr;
     SceneBlob blob{};
     int scene_prec = 0;                 // 0 none, 4 float, 8 double
-    // scratch
-    void *partial = nullptr;
-    size_t partial_bytes = 0;
+    // scratch: fixed-point accumulators of the last render, [pixels][3] int64
+    void *acc = nullptr;
+    size_t acc_bytes = 0;
     void *frame = nullptr;              // device frame when the caller's buffer is host memory
     size_t frame_bytes = 0;
     unsigned long long *queue = nullptr;   // 8 x u64: job cursor + work counters
@@ -675,7 +701,8 @@ struct rt_ctx {
     void *wf_mem = nullptr;
     size_t wf_bytes = 0;
     // uniform grid (RT_ACCEL_GRID, experimental): built on the host the first time it is asked for
-    bool grid_ready = false, grid_usable = false;
+    bool grid_ready = false, grid_usable = false, grid_auto = false;   // usable: the structure fits; auto: RT_ACCEL_AUTO may pick it
+    float grid_build_ms = 0.f;
     GridView grid{};
     void *grid_mem[4] = {nullptr, nullptr, nullptr, nullptr};   // start, items, big_geom, big_slot
     // per-tile candidate lists of the camera rays (rt_primary_bins.cuh), rebuilt by every render call
@@ -845,7 +872,7 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     ctx->bvh_ready = false;
     ctx->bvh = BvhView{};
     for (void *&m : ctx->grid_mem) if (m) { cudaFree(m); m = nullptr; }
-    ctx->grid_ready = ctx->grid_usable = false;
+    ctx->grid_ready = ctx->grid_usable = ctx->grid_auto = false;
     ctx->grid = GridView{};
     ctx->host_geom.clear();
     if (sizeof(T) == 4) {
@@ -894,19 +921,14 @@ int build_lbvh(rt_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     RT_CUDA(cudaEventRecord(ctx->ev[3], st));
 
-    // persistent arrays
+    // persistent arrays; `keep` frees them on every failing exit path, `tmp` releases the device temporaries on every path
     float4 *nodes = nullptr, *geom_sorted = nullptr, *big_geom = nullptr;
     int *slot_sorted = nullptr, *big_slot = nullptr;
-    if (nbig) {
-        std::vector<float4> bg((size_t)nbig);
-        for (int b = 0; b < nbig; ++b) bg[(size_t)b] = g[(size_t)big_idx[(size_t)b]];
-        RT_CUDA(cudaMalloc(&big_geom, sizeof(float4) * nbig));
-        RT_CUDA(cudaMalloc(&big_slot, sizeof(int) * nbig));
-        RT_CUDA(cudaMemcpyAsync(big_geom, bg.data(), sizeof(float4) * nbig, cudaMemcpyHostToDevice, st));
-        RT_CUDA(cudaMemcpyAsync(big_slot, big_idx.data(), sizeof(int) * nbig, cudaMemcpyHostToDevice, st));
-        RT_CUDA(cudaStreamSynchronize(st));
-    }
-    // device temporaries are released on every exit path
+    struct Keep {                       // the arrays that outlive the build; freed here only if the build fails
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool armed = true;
+        ~Keep() { if (armed) for (void *q : p) if (q) cudaFree(q); }
+    } keep;
     struct Scratch {
         std::vector<void *> ptrs;
         ~Scratch() { for (void *p : ptrs) cudaFree(p); }
@@ -916,12 +938,17 @@ int build_lbvh(rt_ctx *ctx) {
             return e;
         }
     } tmp;
-    struct Keep {                       // the arrays that outlive the build; freed here only if the build fails
-        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        bool armed = true;
-        ~Keep() { if (armed) for (void *q : p) if (q) cudaFree(q); }
-    } keep;
-    keep.p[3] = big_geom; keep.p[4] = big_slot;
+    if (nbig) {
+        std::vector<float4> bg((size_t)nbig);
+        for (int b = 0; b < nbig; ++b) bg[(size_t)b] = g[(size_t)big_idx[(size_t)b]];
+        RT_CUDA(cudaMalloc(&big_geom, sizeof(float4) * nbig));
+        keep.p[3] = big_geom;
+        RT_CUDA(cudaMalloc(&big_slot, sizeof(int) * nbig));
+        keep.p[4] = big_slot;
+        RT_CUDA(cudaMemcpyAsync(big_geom, bg.data(), sizeof(float4) * nbig, cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaMemcpyAsync(big_slot, big_idx.data(), sizeof(int) * nbig, cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+    }
     if (m > 0) {
         RT_CUDA(cudaMalloc(&geom_sorted, sizeof(float4) * m));
         keep.p[1] = geom_sorted;
@@ -1016,9 +1043,16 @@ int build_grid(rt_ctx *ctx) {
         const bool fin = std::isfinite(s.x) && std::isfinite(s.y) && std::isfinite(s.z) && std::isfinite(r);
         ((fin && r > 0.0 && r >= 0.25 * r_med && r <= 4.0 * r_med) ? in_grid : big).push_back(i);
     }
-    ctx->grid_ready = true;
-    ctx->grid_usable = in_grid.size() >= 2 && big.size() <= 64;
-    if (!ctx->grid_usable) return RT_OK;
+    if (!(in_grid.size() >= 2 && big.size() <= 64)) {                // not a field of similar spheres
+        ctx->grid_ready = true;
+        ctx->grid_usable = ctx->grid_auto = false;
+        return RT_OK;
+    }
+    const auto t_build0 = std::chrono::steady_clock::now();
+    struct Undo {                                                     // a failed upload leaves no half-built grid behind
+        rt_ctx *c; bool armed = true;
+        ~Undo() { if (armed) { for (void *&m : c->grid_mem) if (m) { cudaFree(m); m = nullptr; } c->grid = GridView{}; } }
+    } undo{ctx};
     double cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     double lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
     double r_max = 0.0, r_min = INFINITY;
@@ -1094,14 +1128,51 @@ int build_grid(rt_ctx *ctx) {
     G.big_slot = static_cast<const int *>(ctx->grid_mem[3]);
     G.nbig = (int)big.size();
     ctx->grid = G;
+    undo.armed = false;
+    ctx->grid_ready = true;
+    ctx->grid_usable = true;
+    // RT_ACCEL_AUTO picks the grid for a planar, compact field: the slab axis is thin against the cell size, and the float-noise
+    // inflation of a ray that starts within two diagonals of the field stays inside half the registration padding, so no
+    // step looks beyond its own cell (grid_closest_hit: k_global == 0) -- measured 53.8 / 49.3 ms against 57.6 ms through the
+    // LBVH on scene 1 at config 2, but 95 ms against 47 ms on the 99 860-slot field, where far cells need rings.
+    double diag2 = 0.0;
+    for (int q = 0; q < 3; ++q) diag2 += (hi3[q] - lo3[q]) * (hi3[q] - lo3[q]);
+    const double reach = 2.0 * std::sqrt(diag2);
+    const double delta_far = (std::sqrt((double)BVH_KEPS * reach * reach + r_min * r_min) - r_min) * 1.001 + 1e-7 + 4.8e-7 * 2.0 * reach;
+    ctx->grid_auto = (hi3[av] - lo3[av]) <= 4.0 * (double)G.h && delta_far <= 0.5 * (double)G.pad && std::isfinite(delta_far);
+    ctx->grid_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
     return RT_OK;
 }
 
-// RT_ACCEL_AUTO -> the faster structure for this scene (same image either way)
-int resolve_accel(const rt_ctx *ctx, int accel) {
-    if (accel != RT_ACCEL_AUTO) return accel;
-    return (ctx->scene_prec == 4 && ctx->blob.n >= 256) ? RT_ACCEL_LBVH : RT_ACCEL_LINEAR;
+// RT_ACCEL_AUTO -> the fastest structure for this scene and these options (same image, bit for bit, whichever is chosen).
+// Float scenes from RT_AUTO_MIN_SLOTS slots up go through the uniform grid when they are a compact field of similar spheres
+// (build_grid: grid_auto) and through the LBVH otherwise; small scenes, double scenes and the wavefront variant keep the
+// shared-memory scan.
+constexpr int RT_AUTO_MIN_SLOTS = 256;
+int resolve_accel(rt_ctx *ctx, const rt_opts &o) {
+    if (o.accel != RT_ACCEL_AUTO) return o.accel;
+    if (ctx->scene_prec != 4 || o.kernel != RT_KERNEL_MEGA) return RT_ACCEL_LINEAR;
+    int min_slots = RT_AUTO_MIN_SLOTS;
+    if (const char *e = getenv("RT_AUTO_MIN_SLOTS")) min_slots = atoi(e);                    // tuning knob
+    if (ctx->blob.n < min_slots) return RT_ACCEL_LINEAR;
+    if (o.primary_bins != RT_PBINS_OFF && !getenv("RT_AUTO_NO_GRID") && build_grid(ctx) == RT_OK && ctx->grid_usable && ctx->grid_auto)
+        return RT_ACCEL_GRID;
+    return RT_ACCEL_LBVH;
 }
+int resolve_accel(rt_ctx *ctx, int accel) {
+    rt_opts o;
+    rt_opts_default(&o);
+    o.accel = accel;
+    return resolve_accel(ctx, o);
+}
+
+// The LBVH is a float structure: these helpers keep the double instantiation of trace() from naming float-only kernels
+// (trace() rejects double + LBVH before it gets here).
+inline void launch_bins_bvh(const DevCamera<float> &cam, const BvhView &bv, int w, int h, int tx, int ty, unsigned int *bins, unsigned grid,
+                            cudaStream_t st) {
+    bin_kernel_bvh<<<grid, 128, 0, st>>>(cam, bv, w, h, tx, ty, bins);
+}
+inline void launch_bins_bvh(const DevCamera<double> &, const BvhView &, int, int, int, int, unsigned int *, unsigned, cudaStream_t) {}
 
 size_t trace_smem(const SceneBlob &b) { return (size_t)b.bytes + (size_t)CAND_CAP * TRACE_BLOCK * sizeof(unsigned short); }
 
@@ -1120,50 +1191,124 @@ template <typename Kernel> int launch_shape(rt_ctx *ctx, Kernel kernel, size_t s
     return RT_OK;
 }
 
-// Wavefront variant: same jobs, same partial planes, two kernels per loop turn over a global pool.
+// ---------------------------------------------------------------------------------------------
+// Job plan (JobPlan, decode_job): how the samples [s_begin, s_begin + s_count) of `rows_local` x `width` pixels are cut into
+// jobs.  Scheduling only -- the image does not depend on it.
+int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out) {
+    JobPlan P{};
+    P.pix_local = (unsigned long long)rows_local * (unsigned long long)width;
+    P.s_begin = s_begin;
+    P.s_count = s_count;
+    if (P.pix_local == 0 || s_count <= 0) { P.total_jobs = 0; *out = P; return RT_OK; }
+    if (P.pix_local > 0xffffffffull) return RT_EINVAL;                     // pixel indices are 32-bit (Philox counter word)
+    int c_a = rt_num_chunks(width, rows_local, s_count);
+    if (const char *e = getenv("RT_CHUNKS")) { const int v = atoi(e); if (v > 0) c_a = v < s_count ? v : s_count; }   // tuning knob
+    int tail_mult = 4;
+    if (const char *e = getenv("RT_TAIL_MULT")) { const int v = atoi(e); if (v > 0) tail_mult = v; }
+    long long c_b = (long long)c_a * tail_mult;
+    if (c_b > s_count) c_b = s_count;
+    // bands: as many rows as keep the band's accumulators (24 B per pixel) within 8 MB of L2
+    long long band_rows = (8ll << 20) / (24ll * width);
+    if (const char *e = getenv("RT_BAND_ROWS")) { const int v = atoi(e); if (v > 0) band_rows = v; }
+    if (band_rows < 1) band_rows = 1;
+    if (band_rows > rows_local) band_rows = rows_local;
+    const unsigned long long band_pix = (unsigned long long)band_rows * width;
+    const unsigned long long bands = (P.pix_local + band_pix - 1) / band_pix;
+    P.band_pix = (unsigned int)band_pix;
+    P.last_pix = (unsigned int)(P.pix_local - (bands - 1) * band_pix);
+    P.chunks[0] = c_a; P.chunks[1] = (int)c_b;
+    for (int r = 0; r < 2; ++r) { P.spp_q[r] = s_count / P.chunks[r]; P.spp_r[r] = s_count % P.chunks[r]; }
+    P.band_jobs = band_pix * (unsigned long long)c_a;
+    P.jobs_a = (bands - 1) * P.band_jobs;
+    P.rp_b = (bands - 1) * band_pix;
+    P.total_jobs = P.jobs_a + (unsigned long long)P.last_pix * (unsigned long long)c_b;
+    auto magic = [](unsigned long long d) { return d > 1 ? ~0ull / d + 1ull : 0ull; };
+    P.magic_band_jobs = magic(P.band_jobs);
+    P.magic_pix[0] = magic(band_pix);
+    P.magic_pix[1] = magic(P.last_pix);
+    P.magic_width = magic((unsigned long long)width);
+    // multiply-high division is exact while dividend * divisor < 2^64; keep a wide margin
+    if ((long double)P.total_jobs * (long double)P.band_jobs >= 9.0e18L) return RT_EINVAL;
+    *out = P;
+    return RT_OK;
+}
+
+// Fills the launch arguments every path-tracing kernel family shares and resets the queue / work counters.
+template <typename T, typename Cam>
+int fill_args(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc, TraceArgs<T> &A) {
+    A.bvh = BvhView{};
+    A.bvh_steps = 0;
+    A.bvh_min_active = 0;
+    A.bins = nullptr;
+    A.tiles_x = 0;
+    A.pb_rounds = 3;                   // measured at config 2 (tools/tune_pbins.sh): 1 round 89-91 ms, 2 rounds 87.5-88, 3+ rounds 86.5-87
+    A.pb_min = 1;
+    if (const char *e = getenv("RT_PB_ROUNDS")) A.pb_rounds = atoi(e) > 0 ? atoi(e) : A.pb_rounds;       // tuning knobs
+    if (const char *e = getenv("RT_PB_MIN")) A.pb_min = atoi(e);
+    A.cam = to_dev<T>(cam);
+    A.scene = ctx->blob;
+    A.keys = philox_keys(o.seed);
+    A.max_depth = cam.max_depth;
+    A.width = cam.width;
+    A.tile_rows = o.tile_rows; A.rank = o.rank;
+    A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
+    const int rc = plan_jobs(cam.width, rows_local, s_begin, s_count, &A.plan);
+    if (rc) return rc;
+    A.acc = acc;
+    A.queue = ctx->queue;
+    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
+    ctx->stats.chunks = A.plan.chunks[0];
+    return RT_OK;
+}
+
+// camera-ray candidate lists of this frame (rt_primary_bins.cuh) into ctx->bins
+template <typename T>
+int build_bins(rt_ctx *ctx, TraceArgs<T> &A, int width, int height, bool from_bvh) {
+    const int tiles_x = (width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
+    const size_t tiles = (size_t)tiles_x * tiles_y;
+    const int rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned int));
+    if (rc) return rc;
+    unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
+    A.bins = bins;
+    A.tiles_x = tiles_x;
+    const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
+    if (from_bvh) launch_bins_bvh(A.cam, ctx->bvh, width, height, tiles_x, tiles_y, bins, bin_grid, ctx->stream);
+    else bin_kernel<T><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n,
+                                                         width, height, tiles_x, tiles_y, bins);
+    RT_CUDA(cudaGetLastError());
+    ctx->stats.launches += 1;
+    return RT_OK;
+}
+
+// Wavefront variant: same jobs, same accumulators, two kernels per loop turn over a global pool.
 template <typename T, typename Cam> struct WavefrontImpl {
-    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, int, typename Num<T>::vec4 *) { return RT_EPRECISION; }
+    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, long long *) { return RT_EPRECISION; }
 };
 template <typename Cam> struct WavefrontImpl<float, Cam> {
-    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, float4 *partial) {
+    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
         const size_t smem_hit = trace_smem(ctx->blob), smem_shade = ctx->blob.bytes;
         if (smem_hit > 227 * 1024 || ctx->blob.n > 65535) return RT_EINVAL;
         TraceArgs<float> A;
-        A.bvh = BvhView{};
-        A.bvh_steps = 0;
-        A.bvh_min_active = 0;
-        A.cam = to_dev<float>(cam);
-        A.scene = ctx->blob;
-        A.keys = philox_keys(o.seed);
-        A.spp = cam.spp; A.max_depth = cam.max_depth;
-        A.width = cam.width;
-        A.tile_rows = o.tile_rows; A.rank = o.rank;
-        A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
-        A.chunks = chunks; A.c_begin = c0;
-        A.spp_q = cam.spp / chunks; A.spp_r = cam.spp % chunks;
-        A.pix_local = (unsigned long long)rows_local * cam.width;
-        A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
-        A.partial = partial;
-        A.queue = ctx->queue;
-        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
-        if (A.total_jobs == 0) return RT_OK;
+        int rc = fill_args<float>(ctx, cam, o, rows_local, s_begin, s_count, acc, A);
+        if (rc) return rc;
+        if (A.plan.total_jobs == 0) return RT_OK;
         // pool: 8 slots per resident thread of the megakernel's shape keeps the state near L2 size
         const unsigned long long want = (unsigned long long)ctx->sm_count * 2048ull * 4ull;
-        const int n = (int)std::min<unsigned long long>(want, (A.total_jobs + 255ull) & ~255ull);
-        const size_t words = 21;                                   // 4-byte arrays (job is 8 bytes = 2 words)
-        const size_t bytes = (size_t)n * 4 * (words + 2 + 2 * WF_CLASSES) + 256;
-        int rc = ensure(&ctx->wf_mem, &ctx->wf_bytes, bytes);
+        const int n = (int)std::min<unsigned long long>(want, (A.plan.total_jobs + 255ull) & ~255ull);
+        const size_t words = 18;                                   // 4-byte arrays per slot
+        const size_t bytes = (size_t)n * 4 * (words + 2 * WF_CLASSES) + 512;
+        rc = ensure(&ctx->wf_mem, &ctx->wf_bytes, bytes);
         if (rc) return rc;
         char *base = static_cast<char *>(ctx->wf_mem);
         auto take = [&](size_t elems, size_t elem_size) { void *p = base; base += ((elems * elem_size + 15) & ~(size_t)15); return p; };
         WfPool P;
         P.n = n;
-        float **fl[] = {&P.ox, &P.oy, &P.oz, &P.dx, &P.dy, &P.dz, &P.ax, &P.ay, &P.az, &P.puy, &P.accr, &P.accg, &P.accb, &P.hit_t};
+        float **fl[] = {&P.ox, &P.oy, &P.oz, &P.dx, &P.dy, &P.dz, &P.ax, &P.ay, &P.az, &P.puy, &P.hit_t};
         for (float **f : fl) *f = static_cast<float *>(take((size_t)n, 4));
         int **in[] = {&P.hit_id, &P.sample, &P.sample_end, &P.depth, &P.state};
         for (int **f : in) *f = static_cast<int *>(take((size_t)n, 4));
         P.pixel = static_cast<uint32_t *>(take((size_t)n, 4));
-        P.job = static_cast<unsigned long long *>(take((size_t)n, 8));
+        P.local = static_cast<uint32_t *>(take((size_t)n, 4));
         int *lists[2] = {static_cast<int *>(take((size_t)n * WF_CLASSES, 4)), static_cast<int *>(take((size_t)n * WF_CLASSES, 4))};
         unsigned int *counts = static_cast<unsigned int *>(take(16, 4));     // [2][4] counts, then alive
         unsigned int *cnt[2] = {counts, counts + WF_CLASSES};
@@ -1201,27 +1346,19 @@ template <typename Cam> struct WavefrontImpl<float, Cam> {
     }
 };
 template <typename T, typename Cam>
-int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
-                    typename Num<T>::vec4 *partial) {
-    return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
+int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
+    return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, s_begin, s_count, acc);
 }
 
-// RT_ACCEL_GRID (experimental, float): camera rays through the tile lists, scattered rays through the uniform grid.
+// RT_ACCEL_GRID (float): camera rays through the tile lists, scattered rays through the uniform grid.
 template <typename T, typename Cam> struct GridImpl {
-    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, int, typename Num<T>::vec4 *) { return RT_EPRECISION; }
+    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, long long *) { return RT_EPRECISION; }
 };
 template <typename T, typename Cam>
-int trace_grid(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, typename Num<T>::vec4 *partial) {
-    return GridImpl<T, Cam>::run(ctx, cam, o, rows_local, chunks, c0, c1, partial);
+int trace_grid(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
+    return GridImpl<T, Cam>::run(ctx, cam, o, rows_local, s_begin, s_count, acc);
 }
 
-// The LBVH is a float structure: these helpers keep the double instantiation of trace() from naming float-only kernels
-// (trace() rejects double + LBVH before it gets here).
-inline void launch_bins_bvh(const DevCamera<float> &cam, const BvhView &bv, int w, int h, int tx, int ty, unsigned int *bins, unsigned grid,
-                            cudaStream_t st) {
-    bin_kernel_bvh<<<grid, 128, 0, st>>>(cam, bv, w, h, tx, ty, bins);
-}
-inline void launch_bins_bvh(const DevCamera<double> &, const BvhView &, int, int, int, int, unsigned int *, unsigned, cudaStream_t) {}
 template <typename T, int ACCEL> void launch_pb(const TraceArgs<T> &A, int grid, size_t smem, cudaStream_t st) {
     if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR) trace_kernel_pb<T, ACCEL><<<grid, TRACE_BLOCK, smem, st>>>(A);
 }
@@ -1231,7 +1368,7 @@ template <typename T, int ACCEL> int shape_pb(rt_ctx *ctx, size_t smem, int *gri
 }
 
 template <typename Cam> struct GridImpl<float, Cam> {
-    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1, float4 *partial) {
+    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
         int rc = build_grid(ctx);
         if (rc) return rc;
         if (!ctx->grid_usable) return RT_EINVAL;                    // not a field of similar spheres: use RT_ACCEL_LBVH
@@ -1239,64 +1376,34 @@ template <typename Cam> struct GridImpl<float, Cam> {
         rc = launch_shape(ctx, trace_kernel_pb<float, RT_ACCEL_GRID>, 0, &grid);
         if (rc) return rc;
         TraceArgs<float> A;
-        A.bvh = BvhView{};
-        A.bvh_steps = 0;
-        A.bvh_min_active = 0;
-        A.pb_rounds = 3;
-        A.pb_min = 1;
-        A.cam = to_dev<float>(cam);
-        A.scene = ctx->blob;
-        A.keys = philox_keys(o.seed);
-        A.spp = cam.spp; A.max_depth = cam.max_depth;
-        A.width = cam.width;
-        A.tile_rows = o.tile_rows; A.rank = o.rank;
-        A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
-        A.chunks = chunks; A.c_begin = c0;
-        A.spp_q = cam.spp / chunks; A.spp_r = cam.spp % chunks;
-        A.pix_local = (unsigned long long)rows_local * cam.width;
-        A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
-        A.magic_pix = A.pix_local > 1 ? ~0ull / A.pix_local + 1ull : 0ull;
-        A.magic_width = cam.width > 1 ? ~0ull / (unsigned long long)cam.width + 1ull : 0ull;
-        A.partial = partial;
-        A.queue = ctx->queue;
-        RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
-        if (A.total_jobs == 0) return RT_OK;
-        const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
-        if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
-        ctx->stats.grid = grid;
-        const int tiles_x = (cam.width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (cam.height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
-        const size_t tiles = (size_t)tiles_x * tiles_y;
-        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned int));
+        rc = fill_args<float>(ctx, cam, o, rows_local, s_begin, s_count, acc, A);
         if (rc) return rc;
-        unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
-        A.bins = bins;
-        A.tiles_x = tiles_x;
-        const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
-        if (ctx->blob.n > 8192) {
-            // large scenes: the tile lists come from a walk of the LBVH (one thread per tile cannot loop over 10^5 slots)
-            rc = build_lbvh(ctx);
-            if (rc) return rc;
-            bin_kernel_bvh<<<bin_grid, 128, 0, ctx->stream>>>(A.cam, ctx->bvh, cam.width, cam.height, tiles_x, tiles_y, bins);
-        } else {
-            bin_kernel<float><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const float4 *>(ctx->blob.base), ctx->blob.n,
-                                                                cam.width, cam.height, tiles_x, tiles_y, bins);
-        }
-        RT_CUDA(cudaGetLastError());
+        if (A.plan.total_jobs == 0) return RT_OK;
+        const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
+        if (A.plan.total_jobs < lanes) grid = (int)((A.plan.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        ctx->stats.grid = grid;
+        // large scenes: the tile lists come from a walk of the LBVH (one thread per tile cannot loop over 10^5 slots)
+        const bool from_bvh = ctx->blob.n > 8192;
+        if (from_bvh) { rc = build_lbvh(ctx); if (rc) return rc; }
+        rc = build_bins<float>(ctx, A, cam.width, cam.height, from_bvh);
+        if (rc) return rc;
         RT_CUDA(cudaMemcpyToSymbolAsync(g_grid, &ctx->grid, sizeof(GridView), 0, cudaMemcpyHostToDevice, ctx->stream));
         trace_kernel_pb<float, RT_ACCEL_GRID><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(A);
         RT_CUDA(cudaGetLastError());
-        ctx->stats.launches += 2;
+        ctx->stats.launches += 1;
         return RT_OK;
     }
 };
 
-// Launches the path tracer for chunks [c0,c1) over `rows_local` rows into `partial`.
+// Launches the path tracer for samples [s_begin, s_begin + s_count) of `rows_local` rows into the accumulators `acc`
+// (which the caller has zeroed).
 template <typename T, typename Cam>
-int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chunks, int c0, int c1,
-          typename Num<T>::vec4 *partial) {
-    if (o.kernel == RT_KERNEL_WAVEFRONT) return trace_wavefront<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
-    if (o.accel == RT_ACCEL_GRID) return trace_grid<T>(ctx, cam, o, rows_local, chunks, c0, c1, partial);
-    const bool lbvh = (resolve_accel(ctx, o.accel) == RT_ACCEL_LBVH);
+int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
+    const int accel = resolve_accel(ctx, o);
+    ctx->stats.accel_used = accel;
+    if (o.kernel == RT_KERNEL_WAVEFRONT) return trace_wavefront<T>(ctx, cam, o, rows_local, s_begin, s_count, acc);
+    if (accel == RT_ACCEL_GRID) return trace_grid<T>(ctx, cam, o, rows_local, s_begin, s_count, acc);
+    const bool lbvh = (accel == RT_ACCEL_LBVH);
     if (lbvh && sizeof(T) != 4) return RT_EPRECISION;
     const size_t smem = lbvh ? 0 : trace_smem(ctx->blob);
     if (smem > 227 * 1024 || (!lbvh && ctx->blob.n > 65535)) return RT_EINVAL;   // too large for the shared-memory scan: use RT_ACCEL_LBVH
@@ -1313,12 +1420,8 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
                               : launch_shape(ctx, trace_kernel<T, RT_ACCEL_LINEAR>, smem, &grid));
     if (rc) return rc;
     TraceArgs<T> A;
-    A.bins = nullptr;
-    A.tiles_x = 0;
-    A.pb_rounds = 3;                   // measured at config 2 (tools/tune_pbins.sh): 1 round 89-91 ms, 2 rounds 87.5-88, 3+ rounds 86.5-87
-    A.pb_min = 1;
-    if (const char *e = getenv("RT_PB_ROUNDS")) A.pb_rounds = atoi(e) > 0 ? atoi(e) : A.pb_rounds;       // tuning knobs
-    if (const char *e = getenv("RT_PB_MIN")) A.pb_min = atoi(e);
+    rc = fill_args<T>(ctx, cam, o, rows_local, s_begin, s_count, acc, A);
+    if (rc) return rc;
     A.bvh = ctx->bvh;
     // node visits per loop turn: about one root-to-leaf descent plus slack (measured: 16 best for 487 spheres,
     // 24 for 99 860); finished lanes are shaded between rounds
@@ -1328,40 +1431,13 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
     A.bvh_min_active = 6;              // measured: +2.4 % on scene 1, +1.4 % on the 99 860-slot scene against 0
     if (const char *e = getenv("RT_BVH_STEPS")) A.bvh_steps = atoi(e) > 0 ? atoi(e) : A.bvh_steps;   // tuning knobs
     if (const char *e = getenv("RT_BVH_MIN_ACTIVE")) A.bvh_min_active = atoi(e);
-    A.cam = to_dev<T>(cam);
-    A.scene = ctx->blob;
-    A.keys = philox_keys(o.seed);
-    A.spp = cam.spp; A.max_depth = cam.max_depth;
-    A.width = cam.width;
-    A.tile_rows = o.tile_rows; A.rank = o.rank;
-    A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
-    A.chunks = chunks; A.c_begin = c0;
-    A.spp_q = cam.spp / chunks; A.spp_r = cam.spp % chunks;
-    A.pix_local = (unsigned long long)rows_local * cam.width;
-    A.total_jobs = A.pix_local * (unsigned long long)(c1 - c0);
-    A.magic_pix = A.pix_local > 1 ? ~0ull / A.pix_local + 1ull : 0ull;       // 0 encodes "divide by 1"
-    A.magic_width = cam.width > 1 ? ~0ull / (unsigned long long)cam.width + 1ull : 0ull;
-    A.partial = partial;
-    A.queue = ctx->queue;
-    RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
-    if (A.total_jobs == 0) return RT_OK;
+    if (A.plan.total_jobs == 0) return RT_OK;
     const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
-    if (A.total_jobs < lanes) grid = (int)((A.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
+    if (A.plan.total_jobs < lanes) grid = (int)((A.plan.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
     ctx->stats.grid = grid;
     if (pbins) {
-        const int tiles_x = (cam.width + (1 << PB_SHIFT) - 1) >> PB_SHIFT, tiles_y = (cam.height + (1 << PB_SHIFT) - 1) >> PB_SHIFT;
-        const size_t tiles = (size_t)tiles_x * tiles_y;
-        rc = ensure(&ctx->bins, &ctx->bins_bytes, tiles * PB_STRIDE * sizeof(unsigned int));
+        rc = build_bins<T>(ctx, A, cam.width, cam.height, lbvh);
         if (rc) return rc;
-        unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
-        A.bins = bins;
-        A.tiles_x = tiles_x;
-        const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
-        if (lbvh) launch_bins_bvh(A.cam, ctx->bvh, cam.width, cam.height, tiles_x, tiles_y, bins, bin_grid, ctx->stream);
-        else bin_kernel<T><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n,
-                                                             cam.width, cam.height, tiles_x, tiles_y, bins);
-        RT_CUDA(cudaGetLastError());
-        ctx->stats.launches += 1;
         if (compact) launch_pb<T, ACCEL_LBVH_COMPACT>(A, grid, smem, ctx->stream);
         else if (lbvh) launch_pb<T, RT_ACCEL_LBVH>(A, grid, smem, ctx->stream);
         else launch_pb<T, RT_ACCEL_LINEAR>(A, grid, smem, ctx->stream);
@@ -1374,12 +1450,11 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int chu
 }
 
 template <typename T>
-int finalize(rt_ctx *ctx, const typename Num<T>::vec4 *partial, int chunks, unsigned long long pix, T scale, T *out_dev,
-             RowPlacement rp = RowPlacement{0, 1, 0, 1}) {
+int finalize(rt_ctx *ctx, const AccSources &src, unsigned long long pix, T scale, T *out_dev, RowPlacement rp = RowPlacement{0, 1, 0, 1}) {
     if (pix == 0) return RT_OK;
     const unsigned long long quads = (pix + 3) / 4;
     const unsigned grid = (unsigned)((quads + 255) / 256);
-    finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(partial, chunks, pix, scale, out_dev, rp);
+    finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(src, pix, scale, out_dev, rp);
     RT_CUDA(cudaGetLastError());
     ctx->stats.launches += 1;
     return RT_OK;
@@ -1389,34 +1464,33 @@ int check_opts(const rt_opts &o) {
     if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return RT_EINVAL;
     if (o.split == RT_SPLIT_ROWS && o.tile_rows < 1) return RT_EINVAL;
     if (o.split < RT_SPLIT_NONE || o.split > RT_SPLIT_SPP) return RT_EINVAL;
-    const bool grid_enabled = getenv("RT_ENABLE_GRID") != nullptr;              // experimental, see rt_grid.cuh
-    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO && !(o.accel == RT_ACCEL_GRID && grid_enabled))
-        return RT_EINVAL;
+    if (o.accel != RT_ACCEL_LINEAR && o.accel != RT_ACCEL_LBVH && o.accel != RT_ACCEL_AUTO && o.accel != RT_ACCEL_GRID) return RT_EINVAL;
     if (o.accel == RT_ACCEL_GRID && (o.kernel != RT_KERNEL_MEGA || o.primary_bins == RT_PBINS_OFF)) return RT_EINVAL;
     if (o.kernel != RT_KERNEL_MEGA && o.kernel != RT_KERNEL_WAVEFRONT) return RT_EINVAL;
     if (o.primary_bins < RT_PBINS_AUTO || o.primary_bins > RT_PBINS_ON) return RT_EINVAL;
-    if (o.kernel == RT_KERNEL_WAVEFRONT && o.accel == RT_ACCEL_LBVH) return RT_EINVAL;
+    if (o.kernel == RT_KERNEL_WAVEFRONT && (o.accel == RT_ACCEL_LBVH || o.accel == RT_ACCEL_GRID)) return RT_EINVAL;
     return RT_OK;
 }
 
-int read_counters(rt_ctx *ctx, float ms_total, float ms_trace, int chunks) {
+int read_counters(rt_ctx *ctx, float ms_total, float ms_trace) {
     unsigned long long h[QUEUE_WORDS];
     RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.segments = h[1];
     ctx->stats.paths = h[2];
-    ctx->stats.sphere_tests = h[3] || h[4] ? h[4] : h[1] * (unsigned long long)ctx->blob.n;
     ctx->stats.node_visits = h[3];
+    ctx->stats.sphere_tests = h[4];
     ctx->stats.binned_segments = h[5];
+    ctx->stats.filter_tests = h[6];
     ctx->stats.render_ms = ms_total;
     ctx->stats.trace_ms = ms_trace;
-    ctx->stats.chunks = chunks;
+    ctx->stats.bvh_build_ms = ctx->bvh_build_ms;
+    ctx->stats.grid_build_ms = ctx->grid_build_ms;
     return RT_OK;
 }
 
 template <typename T, typename Cam>
 int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb, float *render_ms) {
-    using V4 = typename Num<T>::vec4;
     if (!ctx || !cam || !out_rgb) return RT_EINVAL;
     if (!ctx->scene_dev) return RT_ENOSCENE;
     if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
@@ -1432,7 +1506,6 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
                                ? rt_partition_rows(cam->height, o.tile_rows, o.rank, o.world, nullptr, 0)
                                : cam->height;
     const unsigned long long pix = (unsigned long long)rows_local * cam->width;
-    const int chunks = rt_num_chunks(cam->width, cam->height, cam->spp);
     ctx->stats = rt_stats{};
     const size_t out_bytes = (size_t)pix * 3 * sizeof(T);
     const bool out_on_device = is_device_ptr(out_rgb);
@@ -1446,20 +1519,27 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
         if (rc) return rc;
         frame = static_cast<T *>(ctx->frame);
     }
-    RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (cam->max_depth <= 0 && place) return RT_EINVAL;
+    const size_t acc_bytes = (size_t)pix * 3 * sizeof(long long);
+    if (cam->max_depth > 0) {
+        rc = ensure(&ctx->acc, &ctx->acc_bytes, acc_bytes + 16);
+        if (rc) return rc;
+    }
+    RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (cam->max_depth <= 0) {
         // GF camera.h:84,127: no bounce budget -> every path is black
         RT_CUDA(cudaMemsetAsync(frame, 0, out_bytes, ctx->stream));
         RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
         RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     } else {
-        rc = ensure(&ctx->partial, &ctx->partial_bytes, (size_t)pix * chunks * sizeof(V4) + 16);
-        if (rc) return rc;
-        rc = trace<T>(ctx, *cam, o, rows_local, chunks, 0, chunks, static_cast<V4 *>(ctx->partial));
+        RT_CUDA(cudaMemsetAsync(ctx->acc, 0, acc_bytes, ctx->stream));
+        rc = trace<T>(ctx, *cam, o, rows_local, 0, cam->spp, static_cast<long long *>(ctx->acc));
         if (rc) return rc;
         RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        rc = finalize<T>(ctx, static_cast<const V4 *>(ctx->partial), chunks, pix, static_cast<T>(cam->scale), frame, rp);
+        AccSources src{};
+        src.p[0] = static_cast<const long long *>(ctx->acc);
+        src.n = 1;
+        rc = finalize<T>(ctx, src, pix, static_cast<T>(cam->scale), frame, rp);
         if (rc) return rc;
     }
     RT_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1469,7 +1549,7 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
     float ms_total = 0.f, ms_trace = 0.f;
     RT_CUDA(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[2]));
     RT_CUDA(cudaEventElapsedTime(&ms_trace, ctx->ev[0], ctx->ev[1]));
-    rc = read_counters(ctx, ms_total, ms_trace, chunks);
+    rc = read_counters(ctx, ms_total, ms_trace);
     if (rc) return rc;
     if (render_ms) *render_ms = ms_total;
     return RT_OK;
@@ -1484,13 +1564,13 @@ inline void launch_primary_grid(const DevCamera<double> &, const SceneBlob &, co
 template <typename T, typename Cam>
 int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (!ctx || !cam || !ids || !t) return RT_EINVAL;
-    const bool grid = accel == RT_ACCEL_GRID && getenv("RT_ENABLE_GRID") != nullptr;       // experimental, see rt_grid.cuh
-    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH && accel != RT_ACCEL_AUTO && !grid) return RT_EINVAL;
-    if (grid && sizeof(T) != 4) return RT_EPRECISION;
-    if (ctx) accel = resolve_accel(ctx, accel);
-    if (accel == RT_ACCEL_LBVH && sizeof(T) != 4) return RT_EPRECISION;
+    if (cam->width <= 0 || cam->height <= 0) return RT_EINVAL;
+    if (accel != RT_ACCEL_LINEAR && accel != RT_ACCEL_LBVH && accel != RT_ACCEL_AUTO && accel != RT_ACCEL_GRID) return RT_EINVAL;
     if (!ctx->scene_dev) return RT_ENOSCENE;
     if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
+    accel = resolve_accel(ctx, accel);
+    const bool grid = accel == RT_ACCEL_GRID;
+    if ((grid || accel == RT_ACCEL_LBVH) && sizeof(T) != 4) return RT_EPRECISION;
     RT_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)cam->width * cam->height;
     const bool ids_dev = is_device_ptr(ids), t_dev = is_device_ptr(t);
@@ -1551,7 +1631,13 @@ int rt_create(int device, rt_ctx **out) {
     RT_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RT_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return RT_ENODEVICE;                 // sm_100a SASS only: no fallback path
+    // The library carries sm_100a SASS only (no PTX; "a" targets are not forward compatible): any other part, other 10.x
+    // parts included, is refused here rather than at the first launch.
+    if (prop.major != 10 || prop.minor != 0) return RT_ENODEVICE;
+    {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, finalize_kernel<float>) != cudaSuccess) { cudaGetLastError(); return RT_ENODEVICE; }
+    }
     rt_ctx *ctx = new (std::nothrow) rt_ctx;
     if (!ctx) return RT_ENOMEM;
     ctx->device = device;
@@ -1570,7 +1656,7 @@ int rt_destroy(rt_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->scene_dev) cudaFree(ctx->scene_dev);
-    if (ctx->partial) cudaFree(ctx->partial);
+    if (ctx->acc) cudaFree(ctx->acc);
     if (ctx->frame) cudaFree(ctx->frame);
     if (ctx->queue) cudaFree(ctx->queue);
     for (void *m : ctx->bvh_mem) if (m) cudaFree(m);
@@ -1602,8 +1688,8 @@ int rt_render64(rt_ctx *ctx, const rt_camera64 *cam, const rt_opts *opts, double
     return render_impl<double>(ctx, cam, opts, out_rgb, render_ms);
 }
 
-int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts_in, float *partials_dev, float *render_ms) {
-    if (!ctx || !cam || !partials_dev) return RT_EINVAL;
+int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts_in, int64_t *acc_dev, float *render_ms) {
+    if (!ctx || !cam || !acc_dev) return RT_EINVAL;
     if (!ctx->scene_dev) return RT_ENOSCENE;
     if (ctx->scene_prec != 4) return RT_EPRECISION;
     if (cam->width <= 0 || cam->height <= 0 || cam->spp <= 0 || cam->max_depth <= 0) return RT_EINVAL;
@@ -1611,29 +1697,36 @@ int rt_render_partials(rt_ctx *ctx, const rt_camera *cam, const rt_opts *opts_in
     if (opts_in) o = *opts_in; else rt_opts_default(&o);
     int rc = check_opts(o);
     if (rc) return rc;
-    if (!is_device_ptr(partials_dev)) return RT_EINVAL;
+    if (!is_device_ptr(acc_dev)) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
-    const int chunks = rt_num_chunks(cam->width, cam->height, cam->spp);
-    int32_t c0 = 0, c1 = chunks;
-    if (o.split == RT_SPLIT_SPP) { rc = rt_partition_chunks(chunks, o.rank, o.world, &c0, &c1); if (rc) return rc; }
+    int32_t s0 = 0, s1 = cam->spp;
+    if (o.split == RT_SPLIT_SPP) { rc = rt_partition_samples(cam->spp, o.rank, o.world, &s0, &s1); if (rc) return rc; }
     else if (o.split == RT_SPLIT_ROWS) return RT_EINVAL;
     ctx->stats = rt_stats{};
+    const size_t acc_bytes = (size_t)cam->width * cam->height * 3 * sizeof(long long);
     RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = trace<float>(ctx, *cam, o, cam->height, chunks, c0, c1, reinterpret_cast<float4 *>(partials_dev));
+    RT_CUDA(cudaMemsetAsync(acc_dev, 0, acc_bytes, ctx->stream));
+    rc = trace<float>(ctx, *cam, o, cam->height, s0, s1 - s0, reinterpret_cast<long long *>(acc_dev));
     if (rc) return rc;
     RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     RT_CUDA(cudaEventSynchronize(ctx->ev[1]));
     float ms = 0.f;
     RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-    rc = read_counters(ctx, ms, ms, chunks);
+    rc = read_counters(ctx, ms, ms);
     if (rc) return rc;
     if (render_ms) *render_ms = ms;
     return RT_OK;
 }
 
-int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, int chunks, float *out_rgb, float *finalize_ms) {
-    if (!ctx || !cam || !partials_dev || !out_rgb || chunks < 1) return RT_EINVAL;
-    if (!is_device_ptr(partials_dev)) return RT_EINVAL;
+int rt_finalize_sum(rt_ctx *ctx, const rt_camera *cam, const int64_t *const *acc_dev, int n_acc, float *out_rgb, float *finalize_ms) {
+    if (!ctx || !cam || !acc_dev || !out_rgb || n_acc < 1 || n_acc > ACC_SOURCES_MAX) return RT_EINVAL;
+    if (cam->width <= 0 || cam->height <= 0 || cam->spp <= 0) return RT_EINVAL;
+    AccSources src{};
+    for (int g = 0; g < n_acc; ++g) {
+        if (!acc_dev[g] || !is_device_ptr(acc_dev[g])) return RT_EINVAL;
+        src.p[g] = reinterpret_cast<const long long *>(acc_dev[g]);
+    }
+    src.n = n_acc;
     RT_CUDA(cudaSetDevice(ctx->device));
     const unsigned long long pix = (unsigned long long)cam->width * cam->height;
     const size_t out_bytes = (size_t)pix * 3 * sizeof(float);
@@ -1645,7 +1738,7 @@ int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, in
         frame = static_cast<float *>(ctx->frame);
     }
     RT_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = finalize<float>(ctx, reinterpret_cast<const float4 *>(partials_dev), chunks, pix, cam->scale, frame);
+    int rc = finalize<float>(ctx, src, pix, cam->scale, frame);
     if (rc) return rc;
     RT_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!out_on_device) RT_CUDA(cudaMemcpyAsync(out_rgb, frame, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1654,6 +1747,10 @@ int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const float *partials_dev, in
     RT_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     if (finalize_ms) *finalize_ms = ms;
     return RT_OK;
+}
+
+int rt_finalize(rt_ctx *ctx, const rt_camera *cam, const int64_t *acc_dev, float *out_rgb, float *finalize_ms) {
+    return rt_finalize_sum(ctx, cam, &acc_dev, 1, out_rgb, finalize_ms);
 }
 
 int rt_primary_hits(rt_ctx *ctx, const rt_camera *cam, int32_t *ids, float *t) {
@@ -1682,6 +1779,12 @@ int rt_frame_read(rt_ctx *ctx, const void *dev_ptr, void *host_ptr, size_t bytes
     if (!ctx || !dev_ptr || !host_ptr) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
     RT_CUDA(cudaMemcpy(host_ptr, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+int rt_frame_write(rt_ctx *ctx, void *dev_ptr, const void *host_ptr, size_t bytes) {
+    if (!ctx || !dev_ptr || !host_ptr) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMemcpy(dev_ptr, host_ptr, bytes, cudaMemcpyHostToDevice));
     return RT_OK;
 }
 int rt_enable_peer_access(rt_ctx *ctx, int peer_device) {

@@ -72,11 +72,12 @@ __global__ void bvh_leaves_kernel(const float4 *__restrict__ geom, const int *__
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     const float4 g = geom[sorted_slot[k]];
-    geom_sorted[k] = g;
+    geom_sorted[k] = g;                               // the exact test keeps the signed radius (r*r, and 1/r in the normal)
+    const float r = fabsf(g.w);                       // a negative radius is legal in the reference's arithmetic (hollow glass)
     float *b = box + 6 * (size_t)(m - 1 + k);
-    b[0] = g.x - g.w; b[1] = g.y - g.w; b[2] = g.z - g.w;
-    b[3] = g.x + g.w; b[4] = g.y + g.w; b[5] = g.z + g.w;
-    rad[m - 1 + k] = g.w;
+    b[0] = g.x - r; b[1] = g.y - r; b[2] = g.z - r;
+    b[3] = g.x + r; b[4] = g.y + r; b[5] = g.z + r;
+    rad[m - 1 + k] = r;
 }
 
 __device__ __forceinline__ int bvh_delta(const uint32_t *__restrict__ keys, int m, int i, int j) {
@@ -292,6 +293,9 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     }
     if (tl < inf && tr < inf) {
         const bool left_first = tl <= tr;
+        // depth <= 30 Morton bits + the index tie-break of equal keys (log2 m <= 24): at most 54 entries; a full stack would
+        // drop the far child silently, so stop loudly instead
+        if (tv.sp >= BVH_STACK) __trap();
         st.e[tv.sp] = ((unsigned long long)__float_as_uint(left_first ? tr : tl) << 32) | (unsigned int)(left_first ? right : left);
         ++tv.sp;
         tv.node = left_first ? left : right;

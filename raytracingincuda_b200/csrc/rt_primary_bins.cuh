@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(128) bin_kernel_bvh(const __grid_constant__ De
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Persistent path tracer with binned camera rays; the scattered segments go through the shared-memory scan
-// (ACCEL = RT_ACCEL_LINEAR) or the resumable LBVH traversal (RT_ACCEL_LBVH / ACCEL_LBVH_COMPACT, float).  Same jobs, same
-// Philox counters, same partial planes and therefore the same image, bit for bit, as trace_kernel<T, ACCEL>.
+// (ACCEL = RT_ACCEL_LINEAR) or the resumable LBVH traversal (RT_ACCEL_LBVH / ACCEL_LBVH_COMPACT, float).  Same Philox
+// counters per (pixel, sample) and the same integer accumulation, therefore the same image, bit for bit, as trace_kernel<T, ACCEL>.
 //
 // A lane is in one of four phases: FRESH (starts the next sample of its job), HIT (a closest hit waits to be shaded),
 // RAY (a live ray waits for the scan / for its traversal to start), FLY (LBVH: traversal in flight).  One loop turn =
@@ -238,22 +238,19 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     Hit<T> hit;
     hit.t = N::inf();
     hit.id = -1;
-    T acc_r = T(0), acc_g = T(0), acc_b = T(0);
     int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
-    uint32_t pixel = 0, tile = 0;
-    unsigned long long job = 0;
+    uint32_t pixel = 0, local = 0, tile = 0;
     unsigned int n_seg = 0, n_path = 0, n_binned = 0;
+    ScanCount cnt{0u, 0u};
 
-    auto end_path = [&](T cr, T cg, T cb) {
-        acc_r = N::add(acc_r, cr); acc_g = N::add(acc_g, cg); acc_b = N::add(acc_b, cb);
+    auto end_black = [&]() {
         ++n_path;
         phase = FRESH;
-        if (++sample == sample_end) {
-            typename N::vec4 v;
-            v.x = acc_r; v.y = acc_g; v.z = acc_b; v.w = T(0);
-            A.partial[job] = v;
-            state = NEED_JOB;
-        }
+        if (++sample == sample_end) state = NEED_JOB;
+    };
+    auto end_path = [&](T cr, T cg, T cb) {
+        accumulate<T>(A.acc, local, cr, cg, cb);                     // integer atomics: order independent (rt_device.cuh)
+        end_black();
     };
     auto end_in_sky = [&]() {
         T sr, sg, sb;
@@ -275,13 +272,11 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
             if (want) {
                 const unsigned long long claimed = claim_job(A, lane, want);
                 if (state == NEED_JOB) {
-                    if (claimed < A.total_jobs) {
+                    if (claimed < A.plan.total_jobs) {
                         const JobInfo J = decode_job(A, claimed);
-                        job = J.store;                                   // from here on: where the job's sum is stored
-                        pi = J.pi; pj = J.pj; pixel = J.pixel;
+                        pi = J.pi; pj = J.pj; pixel = J.pixel; local = J.local;
                         sample = J.sample; sample_end = J.sample_end;
                         tile = (uint32_t)(pj >> PB_SHIFT) * (uint32_t)A.tiles_x + (uint32_t)(pi >> PB_SHIFT);
-                        acc_r = acc_g = acc_b = T(0);
                         state = ACTIVE;
                         phase = FRESH;
                     } else {
@@ -331,7 +326,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
             ph.open(A.keys, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
             ph.block(0);
             const bool alive = scatter(sc, hit, ph, ps);
-            if (!alive || ++depth >= A.max_depth) end_path(T(0), T(0), T(0));     // GF camera.h:117 / :84,127 -> black
+            if (!alive || ++depth >= A.max_depth) end_black();                    // GF camera.h:117 / :84,127 -> black
             else phase = RAY;
         }
 
@@ -355,33 +350,13 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
             // all 32 lanes take part in the shared-memory scan; the ones without a live ray scan a stale one
             const bool scan = (state == ACTIVE && phase == RAY);
             if (__any_sync(FULL, scan)) {
-                const Hit<T> h = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK);
+                const Hit<T> h = closest_hit<T>(geo, A.scene.n, ps.o, ps.d, cand, TRACE_BLOCK, cnt);
                 if (scan) land(h);
             }
         }
     }
 
-    unsigned long long seg = n_seg, pth = n_path, bnd = n_binned;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        seg += __shfl_xor_sync(FULL, seg, off);
-        pth += __shfl_xor_sync(FULL, pth, off);
-        bnd += __shfl_xor_sync(FULL, bnd, off);
-    }
-    if (lane == 0) {
-        atomicAdd(A.queue + 1, seg);
-        atomicAdd(A.queue + 2, pth);
-        atomicAdd(A.queue + 5, bnd);
-    }
-    if constexpr (LB || GR) {
-        unsigned long long nod = n_nodes, tst = n_tests;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            nod += __shfl_xor_sync(FULL, nod, off);
-            tst += __shfl_xor_sync(FULL, tst, off);
-        }
-        if (lane == 0) { atomicAdd(A.queue + 3, nod); atomicAdd(A.queue + 4, tst); }
-    }
+    flush_counters(A.queue, lane, n_seg, n_path, n_nodes, n_tests + cnt.exact, n_binned, cnt.filt);
 }
 
 }  // namespace rt

@@ -2,9 +2,10 @@
 // variant that sorts by material to cut divergence").  Included by rt_kernels.cu after the
 // shared building blocks (TraceArgs, PathState, camera_ray, scatter, sky, closest_hit).
 //
-// Same state machine as trace_kernel -- a pool slot owns one (pixel, chunk) job at a time and
-// walks its samples in order, so every partial sum and therefore the image is bit-identical to
-// the megakernel's -- but the state lives in a global SoA pool and each loop turn is two kernels:
+// Same state machine as trace_kernel -- a pool slot owns one (pixel, sample range) job at a time, every
+// (pixel, sample) path is the same pure function of the seed and the radiance goes into the same integer
+// accumulators, so the image is bit-identical to the megakernel's -- but the state lives in a global SoA
+// pool and each loop turn is two kernels:
 //
 //   wf_shade      runs over the slots SORTED BY WHAT THEY NEED: [camera ray | lambertian |
 //                 metal | dielectric]; each class is padded to a warp multiple, so every warp
@@ -21,10 +22,9 @@ enum { WF_CLASSES = 4 };                      // 0 camera ray (fresh / needs job
 
 struct WfPool {
     // SoA, `n` slots each
-    float *ox, *oy, *oz, *dx, *dy, *dz, *ax, *ay, *az, *puy, *accr, *accg, *accb, *hit_t;
+    float *ox, *oy, *oz, *dx, *dy, *dz, *ax, *ay, *az, *puy, *hit_t;
     int *hit_id, *sample, *sample_end, *depth, *state;
-    uint32_t *pixel;
-    unsigned long long *job;
+    uint32_t *pixel, *local;
     int n;
     int *list_in, *list_out;                  // [WF_CLASSES][n] slot indices
     unsigned int *count_in, *count_out;       // [WF_CLASSES]
@@ -47,17 +47,11 @@ __device__ __forceinline__ void wf_store_path(const WfPool &P, int s, const Path
 // a path of slot `s` ended with radiance c: accumulate, advance the job (same as trace_kernel's end_path)
 __device__ __forceinline__ int wf_end_path(const TraceArgs<float> &A, const WfPool &P, int s, float cr, float cg, float cb,
                                            unsigned int &n_path) {
-    using N = Num<float>;
-    const float r = N::add(P.accr[s], cr), g = N::add(P.accg[s], cg), b = N::add(P.accb[s], cb);
+    accumulate<float>(A.acc, P.local[s], cr, cg, cb);
     ++n_path;
     const int smp = P.sample[s] + 1;
     P.sample[s] = smp;
-    if (smp == P.sample_end[s]) {
-        A.partial[P.job[s]] = make_float4(r, g, b, 0.0f);
-        return WF_NEED_JOB;
-    }
-    P.accr[s] = r; P.accg[s] = g; P.accb[s] = b;
-    return WF_FRESH;
+    return smp == P.sample_end[s] ? WF_NEED_JOB : WF_FRESH;
 }
 
 // Position of thread `i` in the class-sorted order: classes are padded to warp multiples.
@@ -119,19 +113,14 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ TraceArg
         base = __shfl_sync(0xffffffffu, base, leader);
         if (s >= 0 && state == WF_NEED_JOB) {
             const unsigned long long job = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
-            if (job < A.total_jobs) {
-                const unsigned long long cl = job / A.pix_local;
-                const unsigned long long lp = job - cl * A.pix_local;
-                const int c = A.c_begin + (int)cl;
-                const int lr = (int)(lp / (unsigned long long)A.width);
-                const int pi = (int)(lp - (unsigned long long)lr * A.width);
-                pixel = (uint32_t)global_row(A, lr) * (uint32_t)A.width + (uint32_t)pi;
-                sample = (int)((long long)c * A.spp / A.chunks);
-                P.job[s] = job;
+            if (job < A.plan.total_jobs) {
+                const JobInfo J = decode_job(A, job);
+                pixel = J.pixel;
+                sample = J.sample;
+                P.local[s] = J.local;
                 P.pixel[s] = pixel;
                 P.sample[s] = sample;
-                P.sample_end[s] = (int)((long long)(c + 1) * A.spp / A.chunks);
-                P.accr[s] = 0.0f; P.accg[s] = 0.0f; P.accb[s] = 0.0f;
+                P.sample_end[s] = J.sample_end;
                 state = WF_FRESH;
             } else {
                 state = WF_DEAD;
@@ -163,7 +152,7 @@ __global__ void __launch_bounds__(256) wf_intersect(const __grid_constant__ Trac
     stage_scene(smem, A.scene.base, A.scene.bytes, &bar);
     const SceneView<float> sc = view_of<float>(smem, A.scene);
     unsigned short *cand = reinterpret_cast<unsigned short *>(smem + A.scene.bytes) + threadIdx.x;
-    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene.n);
+    const ScanGeom geo = scan_geom(smem_u32(smem), A.scene);      // the paired filter scan of the megakernel
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < P.n && P.state[s] == WF_HIT;
@@ -172,7 +161,8 @@ __global__ void __launch_bounds__(256) wf_intersect(const __grid_constant__ Trac
     o.x = o.y = o.z = 0.0f;
     d.x = 0.0f; d.y = 1.0f; d.z = 0.0f;
     if (live) { o.x = P.ox[s]; o.y = P.oy[s]; o.z = P.oz[s]; d.x = P.dx[s]; d.y = P.dy[s]; d.z = P.dz[s]; }
-    const Hit<float> hit = closest_hit<float>(geo, A.scene.n, o, d, cand, 256);
+    ScanCount cnt{0u, 0u};
+    const Hit<float> hit = closest_hit<float>(geo, A.scene.n, o, d, cand, 256, cnt);
     int cls = -1;
     unsigned int n_path = 0;
     if (live) {
@@ -200,15 +190,19 @@ __global__ void __launch_bounds__(256) wf_intersect(const __grid_constant__ Trac
             if (cls == c) P.list_out[(size_t)c * P.n + base + __popc(m & ((1u << lane) - 1u))] = s;
         }
     }
-    unsigned long long seg = live ? 1ull : 0ull, pth = n_path;
+    unsigned long long seg = live ? 1ull : 0ull, pth = n_path, ext = cnt.exact, flt = cnt.filt;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         seg += __shfl_xor_sync(0xffffffffu, seg, off);
         pth += __shfl_xor_sync(0xffffffffu, pth, off);
+        ext += __shfl_xor_sync(0xffffffffu, ext, off);
+        flt += __shfl_xor_sync(0xffffffffu, flt, off);
     }
     if (lane == 0) {
         atomicAdd(A.queue + 1, seg);
         if (pth) atomicAdd(A.queue + 2, pth);
+        atomicAdd(A.queue + 4, ext);
+        atomicAdd(A.queue + 6, flt);
         atomicAdd(P.alive, (unsigned int)seg);
     }
 }

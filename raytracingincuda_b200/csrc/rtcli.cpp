@@ -14,10 +14,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <iomanip>
+#include <initializer_list>
 #include <iostream>
 #include <sstream>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -50,13 +52,19 @@ struct Args {
     int scene_id = 0, width = 320, height = 192, samples = 10, bounces = 25, threads = 8;
     // extensions
     unsigned long long seed = 1227;
-    bool use_double = false, no_ppm = false, stats = false, lbvh = false, wavefront = false;
-    int accel = RT_ACCEL_LINEAR;
+    bool use_double = false, no_ppm = false, stats = false, wavefront = false;
+    int accel = RT_ACCEL_AUTO;
     int primary_bins = RT_PBINS_AUTO;
     int gpus = 1, scaled_half = 0;
     std::string split = "rows", prefix, gather = "p2p";
     std::string scene_file, dump_scene;     // general scene loader (float): read the slots from / write them to a text file
 };
+
+// value of an enumerated extension option; anything else fails the way cxxopts fails on a malformed argument
+int to_choice(const std::string &text, std::initializer_list<std::pair<const char *, int>> choices) {
+    for (const auto &c : choices) if (text == c.first) return c.second;
+    die_like_cxxopts("incorrect_argument_type", "Argument '" + text + "' failed to parse");
+}
 
 int to_int(const std::string &name, const std::string &text) {
     char *end = nullptr;
@@ -96,22 +104,23 @@ Args parse(int argc, char **argv) {
         else if (name == "samples") a.samples = to_int(name, value);
         else if (name == "bounces") a.bounces = to_int(name, value);
         else if (name == "threads") a.threads = to_int(name, value);
-        else if (name == "seed") a.seed = std::strtoull(value.c_str(), nullptr, 10);
-        else if (name == "precision") a.use_double = (value == "double");
+        else if (name == "seed") {
+            char *end = nullptr;
+            a.seed = std::strtoull(value.c_str(), &end, 10);
+            if (value.empty() || *end != '\0' || value[0] == '-') die_like_cxxopts("incorrect_argument_type", "Argument '" + value + "' failed to parse");
+        }
+        else if (name == "precision") a.use_double = to_choice(value, {{"float", 0}, {"double", 1}}) != 0;
         else if (name == "gpus") a.gpus = to_int(name, value);
-        else if (name == "split") a.split = value;
+        else if (name == "split") { to_choice(value, {{"rows", 0}, {"spp", 1}}); a.split = value; }
         else if (name == "prefix") a.prefix = value;
-        else if (name == "gather") a.gather = value;
+        else if (name == "gather") { to_choice(value, {{"p2p", 0}, {"host", 1}}); a.gather = value; }
         else if (name == "scene_file") a.scene_file = value;
         else if (name == "dump_scene") a.dump_scene = value;
-        else if (name == "accel") {
-            a.lbvh = (value == "lbvh");
-            // "grid": experimental uniform grid, refused by the library unless RT_ENABLE_GRID=1 (csrc/rt_grid.cuh)
-            a.accel = value == "lbvh" ? (int)RT_ACCEL_LBVH : (value == "auto" ? (int)RT_ACCEL_AUTO : (value == "grid" ? (int)RT_ACCEL_GRID : (int)RT_ACCEL_LINEAR));
-        }
-        else if (name == "kernel") a.wavefront = (value == "wavefront");
-        else if (name == "primary_bins") a.primary_bins = (value == "off") ? RT_PBINS_OFF : RT_PBINS_ON;
-        else if (name == "scaled_half") { a.scaled_half = to_int(name, value); a.lbvh = true; a.accel = RT_ACCEL_LBVH; }
+        else if (name == "accel")
+            a.accel = to_choice(value, {{"auto", RT_ACCEL_AUTO}, {"linear", RT_ACCEL_LINEAR}, {"lbvh", RT_ACCEL_LBVH}, {"grid", RT_ACCEL_GRID}});
+        else if (name == "kernel") a.wavefront = to_choice(value, {{"mega", 0}, {"wavefront", 1}}) != 0;
+        else if (name == "primary_bins") a.primary_bins = to_choice(value, {{"auto", RT_PBINS_AUTO}, {"on", RT_PBINS_ON}, {"off", RT_PBINS_OFF}});
+        else if (name == "scaled_half") a.scaled_half = to_int(name, value);
         else if (name == "no-ppm") a.no_ppm = true;
         else if (name == "stats") a.stats = true;
     }
@@ -147,6 +156,11 @@ int main(int argc, char **argv) {
     }
     if (a.width <= 0 || a.height <= 0 || a.samples <= 0 || a.gpus < 1) {
         std::cerr << "Error: --width/--height/--samples/--gpus must be positive." << "\n";
+        return 1;
+    }
+    const bool spp_split = a.gpus > 1 && a.split == "spp";
+    if (spp_split && (a.use_double || a.bounces <= 0 || a.gpus > 16)) {
+        std::cerr << "Error: --split spp needs --precision float, --bounces > 0 and at most 16 GPUs." << "\n";
         return 1;
     }
 
@@ -191,16 +205,25 @@ int main(int argc, char **argv) {
     CHECK(rt_camera_init(&cam, W, H, a.samples, a.bounces));
     CHECK(rt_camera_init64(&cam64, W, H, a.samples, a.bounces));
 
-    // render (GF main.cu:326-341): one host thread per device, rows interleaved across devices.
-    // With more than one device the frame lives on device 0 and every device stores its finished rows
-    // straight into it over NVLink P2P (rt_opts.place_rows); if peer access is not available the rows go
-    // through host memory instead.
+    // render (GF main.cu:326-341): one host thread per device.
+    //  --split rows (default): rows interleaved across devices; the frame lives on device 0 and every device stores its
+    //    finished rows straight into it over NVLink P2P (rt_opts.place_rows); without peer access (or --gather host) the
+    //    rows go through host memory instead.
+    //  --split spp: every device traces its share of the samples of every pixel into its own int64 accumulation buffer;
+    //    device 0 then adds the buffers inside rt_finalize_sum, reading its peers' memory over NVLink P2P (without peer
+    //    access: through host memory) -- integer sums, so the frame is the single-GPU frame bit for bit either way.
     const size_t frame_bytes = npix * 3 * (a.use_double ? sizeof(double) : sizeof(float));
+    const size_t acc_bytes = npix * 3 * sizeof(int64_t);
     void *frame_dev = nullptr;
     bool p2p = a.gpus > 1 && a.gather != "host";
-    if (p2p) {
+    if (p2p && !spp_split) {
         for (int g = 1; g < a.gpus && p2p; ++g) p2p = rt_enable_peer_access(dev[g].ctx, 0) == RT_OK;
         if (p2p) CHECK(rt_frame_alloc(dev[0].ctx, frame_bytes, &frame_dev));
+    }
+    std::vector<void *> acc(static_cast<size_t>(a.gpus), nullptr);
+    if (spp_split) {
+        for (int g = 1; g < a.gpus && p2p; ++g) p2p = rt_enable_peer_access(dev[0].ctx, g) == RT_OK;
+        for (int g = 0; g < a.gpus; ++g) CHECK(rt_frame_alloc(dev[g].ctx, acc_bytes, &acc[g]));
     }
     std::vector<std::thread> workers;
     std::vector<int> rcs(static_cast<size_t>(a.gpus), RT_OK);
@@ -214,6 +237,12 @@ int main(int argc, char **argv) {
             o.accel = a.accel;
             o.primary_bins = a.primary_bins;
             o.kernel = a.wavefront ? RT_KERNEL_WAVEFRONT : RT_KERNEL_MEGA;
+            if (spp_split) {
+                o.split = RT_SPLIT_SPP; o.rank = g; o.world = a.gpus;
+                rcs[g] = rt_render_partials(d.ctx, &cam, &o, static_cast<int64_t *>(acc[g]), &d.render_ms);
+                rt_get_stats(d.ctx, &d.stats);
+                return;
+            }
             if (a.gpus > 1) { o.split = RT_SPLIT_ROWS; o.rank = g; o.world = a.gpus; o.place_rows = p2p ? 1 : 0; }
             const int nrows = a.gpus > 1 ? rt_partition_rows(H, o.tile_rows, g, a.gpus, nullptr, 0) : H;
             d.rows.resize(static_cast<size_t>(nrows));
@@ -234,7 +263,25 @@ int main(int argc, char **argv) {
     for (int g = 0; g < a.gpus; ++g) CHECK(rcs[g]);
     float render_ms = 0.f;
     for (const auto &d : dev) render_ms = d.render_ms > render_ms ? d.render_ms : render_ms;   // max over devices
-    if (p2p) {
+    if (spp_split) {
+        float fin_ms = 0.f;
+        if (p2p) {
+            std::vector<const int64_t *> list;
+            for (void *p : acc) list.push_back(static_cast<const int64_t *>(p));
+            CHECK(rt_finalize_sum(dev[0].ctx, &cam, list.data(), a.gpus, frame.data(), &fin_ms));
+        } else {
+            // no peer access: add the accumulators on the host (integers: any order), finalize on device 0
+            std::vector<int64_t> total(npix * 3, 0), part(npix * 3);
+            for (int g = 0; g < a.gpus; ++g) {
+                CHECK(rt_frame_read(dev[g].ctx, acc[g], part.data(), acc_bytes));
+                for (size_t k = 0; k < total.size(); ++k) total[k] += part[k];
+            }
+            CHECK(rt_frame_write(dev[0].ctx, acc[0], total.data(), acc_bytes));
+            CHECK(rt_finalize(dev[0].ctx, &cam, static_cast<const int64_t *>(acc[0]), frame.data(), &fin_ms));
+        }
+        render_ms += fin_ms;
+        for (int g = 0; g < a.gpus; ++g) CHECK(rt_frame_free(dev[g].ctx, acc[g]));
+    } else if (p2p) {
         CHECK(rt_frame_read(dev[0].ctx, frame_dev, a.use_double ? static_cast<void *>(frame64.data()) : static_cast<void *>(frame.data()),
                             frame_bytes));
         CHECK(rt_frame_free(dev[0].ctx, frame_dev));
@@ -263,8 +310,11 @@ int main(int argc, char **argv) {
         }
     }
 
-    unsigned long long segments = 0, paths = 0, binned = 0;
-    for (auto &d : dev) { segments += d.stats.segments; paths += d.stats.paths; binned += d.stats.binned_segments; }
+    unsigned long long segments = 0, paths = 0, binned = 0, exact = 0, filt = 0, nodes = 0;
+    for (auto &d : dev) {
+        segments += d.stats.segments; paths += d.stats.paths; binned += d.stats.binned_segments;
+        exact += d.stats.sphere_tests; filt += d.stats.filter_tests; nodes += d.stats.node_visits;
+    }
     const rt_stats st0 = dev[0].stats;
     for (auto &d : dev) rt_destroy(d.ctx);
     const auto e2e_stop = std::chrono::steady_clock::now();
@@ -276,10 +326,11 @@ int main(int argc, char **argv) {
         std::fprintf(stderr,
                      "{\"mpath_samples_per_s\": %.3f, \"paths\": %llu, \"segments\": %llu, \"slots\": %d, "
                      "\"gpus\": %d, \"grid\": %d, \"block\": %d, \"regs\": %d, \"smem_bytes\": %d, \"chunks\": %d, "
-                     "\"accel\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu, \"binned_segments\": %llu}\n",
+                     "\"accel\": \"%s\", \"split\": \"%s\", \"node_visits\": %llu, \"sphere_tests\": %llu, \"filter_tests\": %llu, "
+                     "\"binned_segments\": %llu, \"bvh_build_ms\": %.3f, \"grid_build_ms\": %.3f}\n",
                      mps, paths, segments, n, a.gpus, st0.grid, st0.block, st0.regs, st0.smem_bytes, st0.chunks,
-                     st0.node_visits ? "lbvh" : "linear", (unsigned long long)st0.node_visits, (unsigned long long)st0.sphere_tests,
-                     binned);
+                     st0.accel_used == RT_ACCEL_GRID ? "grid" : (st0.accel_used == RT_ACCEL_LBVH ? "lbvh" : "linear"),
+                     a.gpus > 1 ? a.split.c_str() : "none", nodes, exact, filt, binned, st0.bvh_build_ms, st0.grid_build_ms);
     }
     return 0;
 }

@@ -1,17 +1,17 @@
 """Multi-GPU frame partitioning: one process per GPU over ``torch.distributed``.
 
-The path shards trivially -- pixels and samples are independent and the scene (<= 24 KB) is
-replicated -- so there is no data-path collective inside the render.  The only exchange is the
-final assembly on rank 0 (BASELINE.json north_star):
+The path shards trivially -- pixels and samples are independent and the scene (<= 24 KB, or a few MB with
+its LBVH) is replicated -- so there is no data-path collective inside the render.  The only exchange is
+the final assembly on rank 0 (BASELINE.json north_star):
 
   rows : interleaved tiles of ``tile_rows`` rows, tile t -> rank t mod world.  Each rank renders
          and gamma-encodes its own rows; rank 0 gathers them (NCCL gather over NVLink) and
          scatters them to their row positions.  Philox is keyed by the global pixel index, so the
          assembled frame is bit-identical to the 1-GPU frame.
-  spp  : rank r renders chunks [C*r/world, C*(r+1)/world) of every pixel into linear float4
-         planes; rank 0 gathers the planes and ``rt_finalize`` adds them in chunk order -- the same
-         order the 1-GPU path uses, so this split is bit-identical too (a plain NCCL sum-reduce
-         would not be: its association order is not defined).
+  spp  : rank r renders samples [S*r/world, S*(r+1)/world) of every pixel into the int64 fixed-point
+         accumulation buffer (W*H*3 words); ONE sum-reduce of that buffer (NCCL over NVLink/NVSwitch)
+         delivers the total to rank 0, which scales, gamma-encodes and stores.  The sums are integers, so
+         the reduce is exact in any association order and the frame is bit-identical to the 1-GPU frame.
 
 The functions take a ``render``/``render_partials`` callable so the host logic can be exercised on
 CPU with the gloo backend (tests/test_dist_gloo.py injects the oracle there).
@@ -54,36 +54,14 @@ def render_rows_split(render_rows, width, height, tile_rows, rank, world, device
     return frame
 
 
-def render_spp_split(render_partials, finalize, width, height, chunks, rank, world, device, group=None,
-                     combine="gather"):
-    """``render_partials(planes, c0, c1)`` fills ``planes`` ((c1-c0, width*height, 4) float32 on
-    ``device``) with this rank's chunk sums; ``finalize(all_planes)`` turns the (chunks, W*H, 4)
-    stack into the frame on rank 0.
-
-    combine="gather" (default): rank 0 receives every plane and adds them in chunk order --
-    bit-identical to the 1-GPU frame.  combine="reduce": every rank adds its own planes in chunk
-    order and one NCCL sum-reduce of the W*H*4 accumulation buffer delivers the total to rank 0 --
-    1/world of the traffic, but the association order of the cross-rank sum is NCCL's, so the
-    frame can differ from the canonical one in the last ulp."""
-    bounds = [api.partition_chunks(chunks, r, world) for r in range(world)]
-    c0, c1 = bounds[rank]
-    max_c = max(b[1] - b[0] for b in bounds)
-    local = torch.zeros((max_c, width * height, 4), dtype=torch.float32, device=device)
-    if c1 > c0:
-        render_partials(local[:c1 - c0], c0, c1)
-    if combine == "reduce":
-        acc = local[0].clone()
-        for k in range(1, c1 - c0):
-            acc += local[k]
-        if world > 1:
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM, group=group)
-        return finalize(acc.unsqueeze(0).contiguous()) if rank == 0 else None
-    parts = _gather_to_rank0(local, rank, world, group)
-    if rank != 0:
-        return None
-    if world == 1:
-        planes = local[:chunks]
-    else:
-        planes = torch.cat([p[:b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)
-    return finalize(planes.contiguous())
-
+def render_spp_split(render_partials, finalize, width, height, spp, rank, world, device, group=None):
+    """``render_partials(acc, s0, s1)`` overwrites ``acc`` (a contiguous (height, width, 3) int64 tensor on
+    ``device``) with this rank's fixed-point radiance sums over samples [s0, s1); ``finalize(acc)`` turns the
+    summed accumulators into the frame on rank 0.  Returns the frame on rank 0, None elsewhere."""
+    s0, s1 = api.partition_samples(spp, rank, world)
+    acc = torch.zeros((height, width, 3), dtype=torch.int64, device=device)
+    if s1 > s0:
+        render_partials(acc, s0, s1)
+    if world > 1:
+        dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM, group=group)      # integer sum: exact in any order
+    return finalize(acc) if rank == 0 else None

@@ -2,7 +2,7 @@
 
 Run on the GPU box (the reference-derived binaries under oracle/_ref/ travel with the snapshot;
 /root/reference itself does not exist there):
-    python tests/golden/make_goldens_gpu.py gpurun_out/golden
+    python tests/golden/make_goldens_gpu.py gpurun_out/golden [--only-missing]
 then copy gpurun_out/golden/*.npz into tests/golden/ and commit.
 
   primary_scene{1,2,3}_{f32,f64}.npz   (slot id, t) of the reference's own hit_world() for the
@@ -30,10 +30,10 @@ def read_ppm(path):
     return np.array(tok[4:], dtype=np.int32).reshape(h, w, 3).astype(np.uint8)
 
 
-def main(out_dir):
+def main(out_dir, only_missing=False):
     os.makedirs(out_dir, exist_ok=True)
     tmp = tempfile.mkdtemp()
-    for sid in (1, 2, 3):
+    for sid in (() if only_missing else (1, 2, 3)):
         for tag, suffix, W, H in (("f32", "float", 320, 192), ("f64", "double", 160, 96)):
             dump = os.path.join(tmp, f"scene{sid}_{tag}.dump")
             subprocess.check_call([os.path.join(REF, f"scene_dump_{suffix}"), "--scene_id", str(sid)],
@@ -47,8 +47,13 @@ def main(out_dir):
                                 ids=ids.reshape(H, W).astype(np.int16), t=t.reshape(H, W))
             print("primary", sid, tag, "hits", int((ids >= 0).sum()), "of", n, flush=True)
     jobs = [(1, "float", 320, 192, 4096, 50), (2, "float", 320, 192, 4096, 50), (3, "float", 320, 192, 4096, 50),
-            (1, "double", 320, 192, 1024, 50), (1, "float", 320, 192, 10, 25), (1, "float", 320, 192, 100, 25)]
+            (1, "double", 320, 192, 1024, 50), (1, "float", 320, 192, 10, 25), (1, "float", 320, 192, 100, 25),
+            # round 2: the GlobalDouble renders of all three scenes at the spp the float goldens use
+            (1, "double", 320, 192, 4096, 50), (2, "double", 320, 192, 4096, 50), (3, "double", 320, 192, 4096, 50)]
     for sid, prec, W, H, spp, b in jobs:
+        name = f"ref_scene{sid}_{'f32' if prec == 'float' else 'f64'}_{W}x{H}_{spp}spp_{b}b.npz"
+        if only_missing and os.path.exists(os.path.join(HERE, name)):
+            continue
         exe = os.path.join(REF, f"global-{prec}-cuda-raytrace")
         out = subprocess.check_output([exe, "--scene_id", str(sid), "--width", str(W), "--height", str(H),
                                        "--samples", str(spp), "--bounces", str(b), "--threads", "8"], cwd=tmp)
@@ -63,4 +68,5 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
+    args = [a for a in sys.argv[1:] if a != "--only-missing"]
+    main(args[0] if args else "gpurun_out/golden", only_missing="--only-missing" in sys.argv)

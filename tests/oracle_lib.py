@@ -73,6 +73,13 @@ def lib():
         L.orc_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]
         L.orc_sample64.argtypes = L.orc_sample.argtypes
+        L.orc_fix.restype = C.c_int64
+        L.orc_fix.argtypes = [C.c_double]
+        L.orc_accumulate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]
+        L.orc_accumulate64.argtypes = L.orc_accumulate.argtypes
+        L.orc_finalize.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p]
+        L.orc_finalize64.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -131,6 +138,39 @@ def sample(slots, cam, i, j, s, seed=1227):
     (L.orc_sample64 if double else L.orc_sample)(slots.ctypes.data, len(slots), C.byref(cam), seed,
                                                  i, j, s, rgb.ctypes.data, None)
     return rgb
+
+
+def accumulate(slots, cam, s0=0, s1=None, seed=1227, row0=0, row1=None, acc=None):
+    """Integer accumulators (rows, width, 3) int64 of samples [s0,s1); adds to `acc` when given."""
+    L = lib()
+    double = isinstance(cam, Camera64)
+    row1 = cam.height if row1 is None else row1
+    s1 = cam.spp if s1 is None else s1
+    if acc is None:
+        acc = np.zeros((row1 - row0, cam.width, 3), dtype=np.int64)
+    (L.orc_accumulate64 if double else L.orc_accumulate)(slots.ctypes.data, len(slots), C.byref(cam), seed, row0, row1,
+                                                         s0, s1, acc.ctypes.data, None)
+    return acc
+
+
+def finalize(acc, cam):
+    """Gamma-encoded frame of integer accumulators."""
+    L = lib()
+    double = isinstance(cam, Camera64)
+    acc = np.ascontiguousarray(acc, dtype=np.int64)
+    out = np.empty(acc.shape, dtype=np.float64 if double else np.float32)
+    (L.orc_finalize64 if double else L.orc_finalize)(acc.ctypes.data, acc.size // 3, cam.scale, out.ctypes.data)
+    return out
+
+
+def pixel(slots, cam, i, j, seed=1227):
+    """One gamma-encoded pixel of the canonical image (all cam.spp samples)."""
+    acc = np.zeros(3, dtype=np.int64)
+    for s in range(cam.spp):
+        rgb = sample(slots, cam, i, j, s, seed)
+        for k in range(3):
+            acc[k] += lib().orc_fix(float(rgb[k]))
+    return finalize(acc.reshape(1, 1, 3), cam)[0, 0]
 
 
 def num_chunks(width, height, spp):

@@ -71,26 +71,32 @@ def test_primary_hits_bit_exact_vs_reference_golden(renderer, golden_dir, scene_
     assert np.array_equal(bits(t), bits(g["t"]))
 
 
+@pytest.mark.parametrize("accel", ["linear", "lbvh", "grid", "auto"])
 @pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 48, 32, 12, 25), (2, 64, 40, 16, 50), (3, 40, 24, 9, 50),
                                                      (1, 33, 17, 3, 4)])
-def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth):
+def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth, accel):
+    """Whole frames, bit for bit, against the oracle -- through every structure hit_world can use."""
     slots = rt.scene(scene_id)
     renderer.upload_scene(slots)
     cam = rt.camera(w, h, spp, depth)
-    img = renderer.render(cam)
+    code = {"linear": api.ACCEL_LINEAR, "lbvh": api.ACCEL_LBVH, "grid": api.ACCEL_GRID, "auto": api.ACCEL_AUTO}[accel]
+    img = renderer.render(cam, api.make_opts(accel=code))
     ref, seg = O.render(O.scene(scene_id), O.camera(w, h, spp, depth))
     st = renderer.stats()
     assert st.paths == w * h * spp
     assert st.segments == seg
+    assert st.accel_used == (code if accel != "auto" else (api.ACCEL_GRID if len(slots) >= 256 else api.ACCEL_LINEAR))
     mism = np.argwhere(bits(img) != bits(ref))
     assert len(mism) == 0, f"{len(mism)} differing channels, first {mism[:3]}"
 
 
-def test_render_bit_exact_vs_oracle_double(renderer):
-    renderer.upload_scene(rt.scene(1, double=True))
-    cam = rt.camera(32, 20, 6, 25, double=True)
+@pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 32, 20, 6, 25), (2, 48, 32, 9, 50), (3, 40, 24, 8, 50), (1, 21, 13, 40, 50)])
+def test_render_bit_exact_vs_oracle_double(renderer, scene_id, w, h, spp, depth):
+    """GlobalDouble path (GD camera.h:133-177): whole frames bit for bit against the oracle, scenes 1-3."""
+    renderer.upload_scene(rt.scene(scene_id, double=True))
+    cam = rt.camera(w, h, spp, depth, double=True)
     img = renderer.render(cam)
-    ref, seg = O.render(O.scene(1, True), O.camera(32, 20, 6, 25, double=True))
+    ref, seg = O.render(O.scene(scene_id, True), O.camera(w, h, spp, depth, double=True))
     assert renderer.stats().segments == seg
     assert np.array_equal(bits(img), bits(ref))
 
@@ -124,24 +130,48 @@ def test_row_split_equals_whole_frame(renderer, world):
     assert np.array_equal(bits(out), bits(whole))
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_spp_split_equals_whole_frame(renderer, world):
-    """Chunk partials rendered per rank (RT_SPLIT_SPP) and summed in chunk order give the
-    1-GPU image bit for bit."""
+    """Each rank's int64 accumulation buffer (RT_SPLIT_SPP: its share of the samples) summed in ANY order gives the 1-GPU
+    image bit for bit: torch's integer sum (what the NCCL reduce does) and rt_finalize_sum over the list of buffers (what
+    the CLI does over NVLink P2P) -- and the buffers are the oracle's accumulators."""
     import torch
     renderer.upload_scene(rt.scene(1))
-    cam = rt.camera(64, 40, 40, 25)
+    w, h, spp = 64, 40, 40
+    cam = rt.camera(w, h, spp, 25)
     whole = renderer.render(cam)
-    C = rt.num_chunks(64, 40, 40)
-    planes = torch.zeros((C, 40 * 64, 4), dtype=torch.float32, device="cuda:0")
+    accs = []
     for rank in range(world):
-        c0, c1 = rt.partition_chunks(C, rank, world)
-        o = api.make_opts(split=api.SPLIT_SPP, rank=rank, world=world)
-        if c1 > c0:
-            renderer.render_partials(cam, o, planes[c0:c1])
+        acc = torch.full((h, w, 3), -7, dtype=torch.int64, device="cuda:0")      # rt_render_partials overwrites
+        renderer.render_partials(cam, api.make_opts(split=api.SPLIT_SPP, rank=rank, world=world), acc)
+        accs.append(acc)
+        s0, s1 = rt.partition_samples(spp, rank, world)
+        assert renderer.stats().paths == w * h * (s1 - s0)
     torch.cuda.synchronize()
-    img = renderer.finalize(cam, planes, C)
-    assert np.array_equal(bits(img), bits(whole))
+    want = O.accumulate(O.scene(1), O.camera(w, h, spp, 25), *rt.partition_samples(spp, 1, world))
+    assert np.array_equal(accs[1].cpu().numpy(), want)
+    total = accs[0].clone()
+    for a in reversed(accs[1:]):
+        total += a
+    assert np.array_equal(bits(renderer.finalize(cam, total)), bits(whole))
+    assert np.array_equal(bits(renderer.finalize(cam, accs)), bits(whole))
+    ref, _ = O.render(O.scene(1), O.camera(w, h, spp, 25))
+    assert np.array_equal(bits(whole), bits(ref))
+
+
+@pytest.mark.parametrize("knobs", [{"RT_CHUNKS": "1"}, {"RT_CHUNKS": "7", "RT_TAIL_MULT": "3"}, {"RT_BAND_ROWS": "1"},
+                                   {"RT_BAND_ROWS": "5", "RT_CHUNKS": "40"}])
+def test_image_does_not_depend_on_the_job_partition(renderer, knobs, monkeypatch):
+    """Integer accumulation: however the scheduler cuts pixels into bands and samples into jobs (tuning knobs of
+    plan_jobs), the frame is the same bit for bit."""
+    renderer.upload_scene(rt.scene(3))
+    cam = rt.camera(70, 33, 40, 12)
+    base = renderer.render(cam)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    img = renderer.render(cam)
+    assert renderer.stats().paths == 70 * 33 * 40
+    assert np.array_equal(bits(img), bits(base))
 
 
 @pytest.mark.parametrize("scene_id", [1, 2, 3])
@@ -163,6 +193,34 @@ def test_converged_radiance_vs_reference(renderer, golden_dir, scene_id):
     assert psnr >= 40.0, (psnr, floor_psnr)
     # a bias would show as an error well above the noise floor
     assert (mae <= floor_mae * 1.5 + 0.1).all(), (mae, floor_mae)
+
+
+@pytest.mark.parametrize("scene_id", [1, 2, 3])
+def test_converged_radiance_vs_reference_double(renderer, golden_dir, scene_id):
+    """The double path (rt_render64) against the reference's GlobalDouble PPM (GD camera.h:133-177, material.h:68,
+    vec3.h:120-122; rendered on a B200 by the reference binary rebuilt for sm_100): 320x192, 50 bounces, at 4096 spp
+    (MAE <= 1/255, PSNR >= 40 dB, as for float) or, where only the round-1 golden exists, at 1024 spp -- there the MAE
+    gate of 1/255 sits inside the Monte-Carlo noise of two independent renders (0.8-0.9 code values
+    at 1000 spp), so the gate is widened to 1.25 and tied to the measured two-seed noise floor."""
+    spp = 4096
+    path = os.path.join(golden_dir, f"ref_scene{scene_id}_f64_320x192_{spp}spp_50b.npz")
+    if not os.path.exists(path):
+        spp = 1024
+        path = os.path.join(golden_dir, f"ref_scene{scene_id}_f64_320x192_{spp}spp_50b.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference golden not generated yet")
+    ref = np.load(path)["img"]
+    renderer.upload_scene(rt.scene(scene_id, double=True))
+    cam = rt.camera(320, 192, spp, 50, double=True)
+    a = rt.ppm_quantise(renderer.render(cam).astype(np.float32))
+    b = rt.ppm_quantise(renderer.render(cam, api.make_opts(seed=4242)).astype(np.float32))
+    mae, psnr = image_metrics(a, ref)
+    floor_mae, floor_psnr = image_metrics(a, b)
+    print(f"scene {scene_id} double: vs GlobalDouble MAE {mae} PSNR {psnr:.2f} dB; two-seed floor MAE {floor_mae} PSNR {floor_psnr:.2f} dB")
+    assert psnr >= 40.0, (psnr, floor_psnr)
+    assert (mae <= (1.0 if spp >= 4096 else 1.25)).all(), (mae, floor_mae)   # 1/255; 1024 spp: plus the noise margin
+    assert (mae <= floor_mae * 1.25 + 0.1).all(), (mae, floor_mae)   # a bias would sit well above the floor
+    assert psnr >= floor_psnr - 1.5, (psnr, floor_psnr)
 
 
 def test_full_size_properties(renderer):
@@ -336,9 +394,9 @@ def test_primary_bins_equal_the_full_scan(renderer, scene_id, w, h, spp, depth, 
     returns, so the frames are identical bit for bit -- and equal to the oracle's (which has no bins at all)."""
     renderer.upload_scene(rt.scene(scene_id, double=double))
     cam = rt.camera(w, h, spp, depth, double=double)
-    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
+    on = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_ON))
     st_on = renderer.stats()
-    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     st_off = renderer.stats()
     assert st_on.launches == st_off.launches + 1, "the bin kernel did not run"
     assert (st_on.paths, st_on.segments) == (st_off.paths, st_off.segments)
@@ -356,8 +414,8 @@ def test_primary_bins_on_awkward_scenes(renderer, name):
     slots = AUDIT_SCENES[name]()
     renderer.upload_scene(slots)
     cam = rt.camera(160, 96, 4, 10)
-    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
-    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    on = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_ON))
+    off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     assert np.array_equal(bits(on), bits(off))
 
 
@@ -366,10 +424,10 @@ def test_primary_bins_row_split_and_partial_tiles(renderer):
     columns leave partial tiles at both edges."""
     renderer.upload_scene(rt.scene(1))
     cam = rt.camera(100, 70, 8, 25)
-    whole = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    whole = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     out = np.zeros_like(whole)
     for rank in range(3):
-        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=3, tile_rows=2, primary_bins=api.PBINS_ON)
+        o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=3, tile_rows=2, accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_ON)
         out[rt.partition_rows(cam.height, 2, rank, 3)] = renderer.render(cam, o)
     assert np.array_equal(bits(out), bits(whole))
 
@@ -378,9 +436,9 @@ def test_primary_bins_full_size_frame(renderer):
     """BASELINE config 4's frame (3840x2160, 32 400 tiles, 33 million camera rays at 4 spp): bins on == bins off."""
     renderer.upload_scene(rt.scene(1))
     cam = rt.camera(3840, 2160, 4, 50)
-    on = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_ON))
+    on = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_ON))
     seg_on = renderer.stats().segments
-    off = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     assert renderer.stats().segments == seg_on
     assert np.array_equal(bits(on), bits(off))
 
@@ -391,7 +449,7 @@ def test_primary_bins_lbvh_equal_the_full_traversal(renderer, scene_id, w, h, sp
     without bins, bit for bit, and the work counters agree."""
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    plain = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    plain = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     seg = renderer.stats().segments
     off = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH, primary_bins=api.PBINS_OFF))
     st_off = renderer.stats()
@@ -431,7 +489,7 @@ def test_primary_bins_random_scenes(renderer, seed):
     s["ri"] = np.where(s["type"] == 2, 1.5, 0).astype(np.float32)
     renderer.upload_scene(s)
     cam = rt.camera(160, 96, 4, 8)
-    ref = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    ref = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     for accel in (api.ACCEL_LINEAR, api.ACCEL_LBVH):
         img = renderer.render(cam, api.make_opts(accel=accel, primary_bins=api.PBINS_ON))
         assert np.array_equal(bits(img), bits(ref)), accel
@@ -453,7 +511,7 @@ def test_lbvh_render_equals_linear_scan(renderer, scene_id, w, h, spp, depth):
     """Same hits => same paths => the same image, bit for bit."""
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
+    a = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     seg = renderer.stats().segments
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     st = renderer.stats()
@@ -470,7 +528,7 @@ def test_lbvh_mid_size_scene_equals_linear_scan(renderer):
     ids, t = renderer.primary_hits(cam)
     bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
-    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
+    a = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     assert np.array_equal(bits(a), bits(b))
 
@@ -513,7 +571,7 @@ def test_wavefront_equals_megakernel(renderer, scene_id, w, h, spp, depth):
     path counts."""
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
+    a = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     sa = renderer.stats()
     b = renderer.render(cam, api.make_opts(kernel=api.KERNEL_WAVEFRONT))
     sb = renderer.stats()
@@ -575,7 +633,7 @@ def test_lbvh_random_scenes_equal_linear_scan(renderer, seed):
     ids, t = renderer.primary_hits(cam)
     bids, bt = renderer.primary_hits(cam, accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
-    a = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
+    a = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))       # reference: every segment through the scan
     seg = renderer.stats().segments
     b = renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH))
     assert renderer.stats().segments == seg
@@ -675,7 +733,7 @@ def test_config4_frame_size_properties(renderer):
     whole = torch.empty((H, W, 3), dtype=torch.float32, device="cuda:0")
     renderer.render(cam, out=whole)
     st = renderer.stats()
-    assert st.paths == W * H * 4 and st.chunks == 4 and 2.0 < st.segments / st.paths < 4.0
+    assert st.paths == W * H * 4 and st.chunks == rt.num_chunks(W, H, 4) and 2.0 < st.segments / st.paths < 4.0
     placed = torch.zeros_like(whole)
     for rank in range(8):
         o = api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=8)
@@ -683,15 +741,56 @@ def test_config4_frame_size_properties(renderer):
         renderer.render(cam, o, out=placed)
     assert torch.equal(placed.view(torch.int32), whole.view(torch.int32))
     lb = torch.empty_like(whole)
-    renderer.render(cam, api.make_opts(accel=api.ACCEL_LBVH), out=lb)
-    assert renderer.stats().segments == st.segments
+    for accel in (api.ACCEL_LINEAR, api.ACCEL_LBVH, api.ACCEL_GRID):
+        renderer.render(cam, api.make_opts(accel=accel), out=lb)
+        assert renderer.stats().segments == st.segments
+        assert torch.equal(lb.view(torch.int32), whole.view(torch.int32)), accel
+    # 8-way spp split: eight int64 accumulation buffers, added inside rt_finalize_sum
+    cam8 = rt.camera(W, H, 8, 50)
+    renderer.render(cam8, out=whole)
+    accs = []
+    for rank in range(8):
+        acc = torch.empty((H, W, 3), dtype=torch.int64, device="cuda:0")
+        renderer.render_partials(cam8, api.make_opts(split=api.SPLIT_SPP, rank=rank, world=8), acc)
+        accs.append(acc)
+    renderer.finalize(cam8, accs, out=lb)
     assert torch.equal(lb.view(torch.int32), whole.view(torch.int32))
+    del accs
+    renderer.render(cam, out=whole)
     img = whole.cpu().numpy()
     assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 1.0001
     ids, t = renderer.primary_hits(rt.camera(W, H))
     bids, bt = renderer.primary_hits(rt.camera(W, H), accel=api.ACCEL_LBVH)
     assert np.array_equal(ids, bids) and np.array_equal(bits(t), bits(bt))
     assert len(np.unique(ids)) > 100                      # the 20-degree view sees about 140 of the 488 slots
+
+
+@pytest.mark.parametrize("w,h,spp,depth,double", [(1920, 1080, 100, 25, False), (3840, 2160, 1000, 50, False),
+                                                   (1920, 1080, 100, 50, True)])
+def test_full_size_frame_spot_check_vs_oracle(renderer, w, h, spp, depth, double):
+    """BASELINE configs 2, 3 and 4 at FULL size (config 4: 8.3 G path-samples, 265 M jobs -- the size where the job decode's
+    64-bit multiply-high divisions and the band / tail-region arithmetic matter): the frame is rendered once on the device
+    and random pixels, the four corners and the first / last pixel of bands are recomputed sample by sample with the
+    oracle (orc_sample + integer accumulation) and compared bit for bit."""
+    import torch
+    scene_id = 1 if not double else 2
+    renderer.upload_scene(rt.scene(scene_id, double=double))
+    cam = rt.camera(w, h, spp, depth, double=double)
+    frame = torch.empty((h, w, 3), dtype=torch.float64 if double else torch.float32, device="cuda:0")
+    renderer.render(cam, out=frame)
+    st = renderer.stats()
+    assert st.paths == w * h * spp
+    rng = np.random.default_rng(w + spp)
+    n_rand = 40 if spp <= 100 else 20
+    pts = [(0, 0), (w - 1, 0), (0, h - 1), (w - 1, h - 1), (w // 2, h // 2), (w - 1, h // 2), (0, h // 3)]
+    pts += [(int(rng.integers(0, w)), int(rng.integers(0, h))) for _ in range(n_rand)]
+    oslots, ocam = O.scene(scene_id, double), O.camera(w, h, spp, depth, double=double)
+    ys = torch.tensor([p[1] for p in pts], device="cuda:0")
+    xs = torch.tensor([p[0] for p in pts], device="cuda:0")
+    got = frame[ys, xs].cpu().numpy()
+    for k, (i, j) in enumerate(pts):
+        want = O.pixel(oslots, ocam, i, j)
+        assert np.array_equal(bits(got[k]), bits(want)), (i, j, got[k], want)
 
 
 def test_invalid_inputs_fail_loudly(renderer):
@@ -725,27 +824,51 @@ def test_invalid_inputs_fail_loudly(renderer):
     assert e.value.code == -1                              # RT_EINVAL
 
 
-# ------------------------------------------------- RT_ACCEL_GRID (experimental, next round) ------
-# The uniform-grid closest hit is validated on the CPU (tests/test_grid_model.py); its CUDA transcription has not run on
-# hardware yet, so the library refuses it unless RT_ENABLE_GRID=1 -- and so do these tests.
-grid_enabled = pytest.mark.skipif(not os.environ.get("RT_ENABLE_GRID"), reason="RT_ACCEL_GRID is experimental: set RT_ENABLE_GRID=1")
+# ------------------------------------------------------------------ uniform grid (RT_ACCEL_GRID) ------
+# The algorithm is also stated operation by operation in float32 in tools/grid_model.py and checked on the CPU against the
+# oracle's hit_world (tests/test_grid_model.py).
+GRID_SCENES = {"scene1": lambda: rt.scene(1), "scene2": lambda: rt.scene(2), "scene3": lambda: rt.scene(3),
+               "shifted": lambda: shifted_scene(1.0, (37.0, 3.0, -21.0)), "scaled24": lambda: rt.scene_scaled(24),
+               "scaled158": lambda: rt.scene_scaled(158)}
 
 
-def test_grid_is_refused_unless_enabled(renderer):
-    if os.environ.get("RT_ENABLE_GRID"):
-        pytest.skip("enabled in this environment")
-    renderer.upload_scene(rt.scene(2))
+def test_grid_is_refused_for_a_scene_that_is_not_a_field(renderer):
+    """One sphere plus the ground: no two similar spheres -> RT_EINVAL for RT_ACCEL_GRID, while AUTO renders it."""
+    s = rt.scene(1)[:2].copy()
+    s["r"][1] = 30.0
+    renderer.upload_scene(s)
     with pytest.raises(rt.RtError) as e:
         renderer.render(rt.camera(16, 16, 1, 2), api.make_opts(accel=api.ACCEL_GRID))
     assert e.value.code == -1                              # RT_EINVAL
+    img = renderer.render(rt.camera(16, 16, 1, 2))
+    assert renderer.stats().accel_used == api.ACCEL_LINEAR and np.isfinite(img).all()
 
 
-@grid_enabled
-@pytest.mark.parametrize("name", ["scene1", "scene2", "scene3", "shifted", "scaled24", "scaled158"])
+def test_auto_picks_grid_lbvh_linear(renderer):
+    """RT_ACCEL_AUTO: the compact planar field of scene 1 -> grid; the 99 860-slot field (far cells need rings) and a 3-D
+    soup -> LBVH; small and double scenes -> linear scan."""
+    cam = rt.camera(32, 20, 1, 4)
+    for slots, want in ((rt.scene(1), api.ACCEL_GRID), (rt.scene(3), api.ACCEL_LINEAR), (rt.scene_scaled(158), api.ACCEL_LBVH),
+                        (rt.scene_scaled(12), api.ACCEL_GRID)):
+        renderer.upload_scene(slots)
+        renderer.render(cam)
+        assert renderer.stats().accel_used == want, (len(slots), renderer.stats().accel_used)
+    rng = np.random.default_rng(5)
+    s = np.zeros(600, dtype=api.SLOT_DTYPE)
+    s["c"] = rng.uniform(-8, 8, (600, 3)).astype(np.float32)
+    s["r"] = 0.2
+    s["albedo"] = 0.5
+    renderer.upload_scene(s)
+    renderer.render(cam)
+    assert renderer.stats().accel_used == api.ACCEL_LBVH
+    renderer.upload_scene(rt.scene(1, double=True))
+    renderer.render(rt.camera(32, 20, 1, 4, double=True))
+    assert renderer.stats().accel_used == api.ACCEL_LINEAR
+
+
+@pytest.mark.parametrize("name", sorted(GRID_SCENES))
 def test_grid_primary_equals_linear_scan(renderer, name):
-    slots = {"scene1": lambda: rt.scene(1), "scene2": lambda: rt.scene(2), "scene3": lambda: rt.scene(3),
-             "shifted": lambda: shifted_scene(1.0, (37.0, 3.0, -21.0)), "scaled24": lambda: rt.scene_scaled(24),
-             "scaled158": lambda: rt.scene_scaled(158)}[name]()
+    slots = GRID_SCENES[name]()
     renderer.upload_scene(slots)
     cam = rt.camera(320, 192)
     gids, gt = renderer.primary_hits(cam, accel=api.ACCEL_GRID)
@@ -753,14 +876,52 @@ def test_grid_primary_equals_linear_scan(renderer, name):
     assert np.array_equal(gids, ids) and np.array_equal(bits(gt), bits(t))
 
 
-@grid_enabled
 @pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 320, 192, 8, 25), (2, 200, 120, 8, 50), (3, 97, 61, 12, 50)])
 def test_grid_render_equals_linear_scan(renderer, scene_id, w, h, spp, depth):
     renderer.upload_scene(rt.scene(scene_id))
     cam = rt.camera(w, h, spp, depth)
-    ref = renderer.render(cam, api.make_opts(primary_bins=api.PBINS_OFF))
+    ref = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
     seg = renderer.stats().segments
     img = renderer.render(cam, api.make_opts(accel=api.ACCEL_GRID))
     st = renderer.stats()
     assert st.segments == seg and 0 < st.sphere_tests < seg * 40
     assert np.array_equal(bits(img), bits(ref))
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24, 25, 26])
+def test_grid_random_fields_equal_linear_scan(renderer, seed):
+    """Random fields of similar spheres (jittered lattice, radii within a factor 3, tilted or raised slabs, a few odd-sized
+    spheres, an exact duplicate, the ground): grid and linear renders and primary passes must be bit-equal; spheres of
+    negative radius (the hollow-glass idiom: r*r in the reference's arithmetic) included."""
+    rng = np.random.default_rng(seed)
+    side = int(rng.integers(6, 40))
+    n = side * side + 4
+    s = np.zeros(n, dtype=api.SLOT_DTYPE)
+    gx, gz = np.meshgrid(np.arange(side), np.arange(side))
+    pitch = float(rng.choice([0.6, 1.0, 2.5]))
+    s["c"][:side * side, 0] = (gx.ravel() - side / 2) * pitch + rng.uniform(-0.4, 0.4, side * side) * pitch
+    s["c"][:side * side, 2] = (gz.ravel() - side / 2) * pitch + rng.uniform(-0.4, 0.4, side * side) * pitch
+    s["c"][:side * side, 1] = 0.2 + rng.uniform(0, float(rng.choice([0.0, 0.5, 3.0])), side * side)
+    s["r"][:side * side] = 0.2 * np.exp(rng.uniform(np.log(0.6), np.log(1.8), side * side))
+    s["r"][3] = -s["r"][3]                                      # negative radius
+    s["c"][-4] = (0, -1000, 0); s["r"][-4] = 1000
+    s["c"][-3] = (0, 1, 0); s["r"][-3] = 1.0
+    s["c"][-2] = (-4, 1, 0); s["r"][-2] = 0.004                  # far smaller than the field's spheres
+    s[-1] = s[7]                                                 # exact duplicate: tie on t, lowest slot wins
+    s["type"] = rng.integers(0, 3, n)
+    s["type"][-4] = 0
+    s["albedo"] = rng.uniform(0.2, 1.0, (n, 3)).astype(np.float32)
+    s["fuzz"] = np.where(s["type"] == 1, rng.uniform(0, 0.5, n), 0).astype(np.float32)
+    s["ri"] = np.where(s["type"] == 2, 1.5, 0).astype(np.float32)
+    renderer.upload_scene(s)
+    cam = rt.camera(96, 64, 6, 12)
+    ids, t = renderer.primary_hits(cam)
+    for accel in (api.ACCEL_GRID, api.ACCEL_LBVH):
+        gids, gt = renderer.primary_hits(cam, accel=accel)
+        assert np.array_equal(ids, gids) and np.array_equal(bits(t), bits(gt)), accel
+    a = renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR, primary_bins=api.PBINS_OFF))
+    seg = renderer.stats().segments
+    for accel in (api.ACCEL_GRID, api.ACCEL_LBVH, api.ACCEL_AUTO):
+        b = renderer.render(cam, api.make_opts(accel=accel))
+        assert renderer.stats().segments == seg
+        assert np.array_equal(bits(a), bits(b)), accel

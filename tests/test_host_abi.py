@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in rt_b200.h but not exported"
     assert sorted(api.SYMBOLS) == names, "api.SYMBOLS and the header drifted apart"
-    assert rt.lib().rt_abi_version() == 2
+    assert rt.lib().rt_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -90,11 +90,14 @@ def test_partitions():
             rows = rt.partition_rows(h, tile, r, world)
             assert (np.diff(rows) > 0).all()
             assert all((j // tile) % world == r for j in rows)
-    for c, world in [(8, 1), (8, 2), (8, 4), (8, 8), (72, 8), (5, 8)]:
-        b = [rt.partition_chunks(c, r, world) for r in range(world)]
-        assert b[0][0] == 0 and b[-1][1] == c and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    for spp, world in [(8, 1), (8, 2), (1000, 4), (1000, 8), (1000, 3), (72, 8), (5, 8)]:
+        b = [rt.partition_samples(spp, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == spp and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert max(x[1] - x[0] for x in b) - min(x[1] - x[0] for x in b) <= 1
     with pytest.raises(rt.RtError):
         rt.partition_rows(10, 8, 2, 2)
+    with pytest.raises(rt.RtError):
+        rt.partition_samples(10, 2, 2)
     assert rt.num_chunks(3840, 2160, 1000) == 32 and rt.num_chunks(320, 192, 4096) == 128
     for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 10), (320, 192, 4096), (320, 192, 5), (8, 8, 100000),
                       (7680, 4320, 100000), (640, 360, 17), (3840, 2160, 256), (97, 61, 12)]:

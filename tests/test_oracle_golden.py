@@ -134,15 +134,16 @@ def test_hit_world_edge_cases():
     assert hit == -1                                       # empty world
 
 
-def test_chunk_layout():
-    assert O.num_chunks(3840, 2160, 1000) == 32              # at most 32 samples per job
-    assert O.num_chunks(1920, 1080, 100) == 8
-    assert O.num_chunks(320, 192, 10) == 8
+def test_job_granularity():
+    """Sample ranges per pixel are scheduling only (the accumulation is an integer sum): jobs of at most 32 samples, more
+    and shorter jobs on small frames, never more ranges than samples."""
+    assert O.num_chunks(3840, 2160, 1000) == 32
+    assert O.num_chunks(1920, 1080, 100) == 4
+    assert O.num_chunks(320, 192, 10) == 10
     assert O.num_chunks(320, 192, 4096) == 128
     assert O.num_chunks(3840, 2160, 256) == 8
-    assert O.num_chunks(7680, 4320, 100000) == 16            # partial planes stay below 8 GiB
     assert O.num_chunks(320, 192, 5) == 5
-    assert O.num_chunks(8, 8, 100000) == 1024
+    assert O.num_chunks(8, 8, 100000) == 4096
     for spp in (9, 17, 100, 1000):
         c = O.num_chunks(640, 360, spp)
         edges = [k * spp // c for k in range(c + 1)]
@@ -150,32 +151,49 @@ def test_chunk_layout():
 
 
 def test_chunk_edges_without_the_wide_division():
-    """The kernels compute a chunk's first sample as c*(spp // C) + c*(spp % C) // C in 32-bit arithmetic (rt_kernels.cu
-    first_sample); it must equal floor(c * spp / C), the oracle's edge, and c * (spp % C) must stay below 2^31."""
+    """The kernels compute a range's first sample as c*(S // C) + c*(S % C) // C in 32-bit arithmetic (rt_kernels.cu
+    decode_job); it must equal floor(c * S / C), and c * (S % C) must stay below 2^31 -- also for the four-times finer
+    ranges of the last band."""
     for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 4096), (8, 8, 100000), (640, 360, 17), (97, 61, 1023),
                       (7680, 4320, 100000), (64, 40, 2147483647)]:
-        C = O.num_chunks(w, h, spp)
-        q, r = divmod(spp, C)
-        assert C <= 1024 and C * r < 2 ** 31
-        for c in list(range(0, C + 1, max(1, C // 37))) + [C]:
-            assert c * q + (c * r) // C == (c * spp) // C
+        for mult in (1, 4):
+            C = min(O.num_chunks(w, h, spp) * mult, spp)
+            q, r = divmod(spp, C)
+            assert C <= 16384 and (C + 1) * r < 2 ** 31
+            for c in list(range(0, C + 1, max(1, C // 37))) + [C]:
+                assert c * q + (c * r) // C == (c * spp) // C
+
+
+def test_fixed_point_accumulation():
+    """fix40: round-to-nearest-even of v * 2^40, saturating, NaN -> 0; exact for the floats a path returns."""
+    L = O.lib()
+    assert L.orc_fix(0.0) == 0 and L.orc_fix(1.0) == 1 << 40 and L.orc_fix(-0.5) == -(1 << 39)
+    assert L.orc_fix(float(np.float32(0.7))) == int(np.float64(np.float32(0.7)) * 2.0 ** 40)      # exact: 24-bit mantissa
+    assert L.orc_fix(2.0 ** -41) == 0 and L.orc_fix(3 * 2.0 ** -41) == 2                           # ties to even
+    assert L.orc_fix(float("nan")) == 0
+    assert L.orc_fix(1e30) == 2 ** 63 - 1 and L.orc_fix(-1e30) == -2 ** 63
+    assert L.orc_fix(float("inf")) == 2 ** 63 - 1
 
 
 def test_render_sample_decomposition_and_rows():
-    """render == per-pixel chunked sum of orc_sample, and row bands tile the frame."""
+    """render == integer sum of fix40(orc_sample) per pixel, in any order, then scale + gamma; row bands and sample
+    ranges tile the frame."""
     s = O.scene(3)
     cam = O.camera(16, 10, 9, 25)
     img, seg = O.render(s, cam)
-    c = O.num_chunks(16, 10, 9)
-    acc = np.zeros(3, dtype=np.float32)
-    for k in range(c):
-        part = np.zeros(3, dtype=np.float32)
-        for smp in range(k * 9 // c, (k + 1) * 9 // c):
-            part = part + O.sample(s, cam, 5, 7, smp)
-        acc = acc + part
-    v = acc * np.float32(cam.scale)
+    acc = [0, 0, 0]
+    for smp in (8, 2, 5, 0, 7, 1, 3, 6, 4):                     # any order
+        rgb = O.sample(s, cam, 5, 7, smp)
+        for k in range(3):
+            acc[k] += O.lib().orc_fix(float(rgb[k]))
+    lin = (np.array(acc, dtype=np.float64) * 2.0 ** -40).astype(np.float32)
+    v = lin * np.float32(cam.scale)
     want = np.where(v > 0, np.sqrt(v), np.float32(0)).astype(np.float32)
     assert np.array_equal(bits(img[7, 5]), bits(want))
+    assert np.array_equal(bits(O.pixel(s, cam, 5, 7)), bits(want))
+    a = O.accumulate(s, cam, 4, 9)
+    O.accumulate(s, cam, 0, 4, acc=a)
+    assert np.array_equal(bits(O.finalize(a, cam)), bits(img))
     top, _ = O.render(s, cam, row0=0, row1=4)
     bot, _ = O.render(s, cam, row0=4, row1=10)
     assert np.array_equal(bits(np.concatenate([top, bot])), bits(img))
