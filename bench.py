@@ -5,10 +5,16 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full render of the workload (default: BASELINE config 4, scene 1, 3840x2160,
-1000 spp, 50 bounces, float).  `value` = W*H*spp*1e-6 / step-seconds (Mpath-samples/s), timed with
+1000 spp, 50 bounces, float) through the library's DEFAULT options (rt_opts_default: RT_ACCEL_AUTO --
+what a user of the drop-in gets).  `value` = W*H*spp*1e-6 / step-seconds (Mpath-samples/s), timed with
 CUDA events on the launching stream, scene already resident in HBM, max over ranks.  `e2e` is the
 same metric through the public C-ABI call with HOST buffers: per step the scene slots are uploaded
 from host memory and the gamma-encoded frame is read back into pinned host memory.
+Besides the headline the same JSON line carries (N = 1) every other BASELINE config (`configs`: config 2,
+config 3 scenes 2 and 3 in float and double, config 5), the shared-memory linear scan on the headline workload
+with its executed-FP32 roofline (`linear_scan`: the kernel the north star's FP32-pipe target is about), the CPU
+baseline, the reference's own GPU kernels rebuilt for sm_100 and the CLI's stdout contract at 4K; and (N > 1) both
+multi-GPU partitionings (`splits`) and config 5 on N GPUs.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -44,7 +50,9 @@ def workload_name(name):
     what = (f"scaled random-spheres scene, grid [-{-scene},{-scene})^2 ({1 + 4 * scene * scene + 3} slots)" if scene < 0
             else f"scene {scene} final random spheres ({SLOTS[scene]} slots)")
     return f"{what}, {W}x{H}, {spp} spp, {depth} bounces"
-FLOP_PER_TEST = 18          # 3 FADD + 3 FMUL + 6 FFMA per sphere test
+FLOP_PER_TEST = 18          # 3 FADD + 3 FMUL + 6 FFMA per exact sphere test (the reference's arithmetic)
+FLOP_PER_FILTER = 14        # the scan's conservative filter: 7 FMA per (ray, slot) test
+FLOP_PER_NODE = {"lbvh": 52, "grid": 24}   # two inflated slab tests per LBVH node visit; cell exit + index arithmetic per grid cell
 SM_COUNT, FP32_LANES = 148, 128
 
 
@@ -55,15 +63,14 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
-    ap.add_argument("--split", default="rows", choices=["rows", "spp"])
-    ap.add_argument("--spp-combine", default="gather", choices=["gather", "reduce"],
-                    help="spp split: ordered gather (bit-exact) or NCCL sum-reduce of the accumulation buffer")
+    ap.add_argument("--split", default="rows", choices=["rows", "spp"], help="headline partitioning for --gpus > 1")
     ap.add_argument("--tile-rows", type=int, default=1)
-    ap.add_argument("--accel", default="linear", choices=["linear", "lbvh", "grid"],
-                    help="grid: experimental (csrc/rt_grid.cuh), needs RT_ENABLE_GRID=1")
+    ap.add_argument("--accel", default="auto", choices=["auto", "linear", "lbvh", "grid"],
+                    help="auto (default) = rt_opts_default: what the drop-in binary uses")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
-    ap.add_argument("--no-lbvh-extra", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no configs / linear_scan / splits blocks")
+    ap.add_argument("--no-lbvh-extra", action="store_true", help=argparse.SUPPRESS)      # old name of --no-extras
     return ap.parse_args()
 
 
@@ -198,39 +205,67 @@ def run_reference_arm(args):
     }))
 
 
-# ------------------------------------------------------------------ reference kernel on the GPU
-def reference_gpu_kernel():
-    """The reference's kernels rebuilt for sm_100 (oracle/_ref), BASELINE config 2, their own render_ms stdout field:
-    the global-float variant (the parity target) and, as timing comparators only, the constant- and texture-memory
-    variants the shared-memory scene replaces (scene 1 only, ConstFloat main.cu:73-76)."""
+# ------------------------------------------------------------------ reference kernels on the GPU
+def _run_ref(exe_name, scene, W, H, spp, depth, runs):
+    """render_ms values (the reference's own stdout field, GF main.cu:342-343) of `runs` runs of a rebuilt reference binary."""
+    exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
+    if not os.path.exists(exe):
+        return None
+    out_ms, e2e = [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        for _ in range(runs):
+            out = subprocess.check_output([exe, "--scene_id", str(scene), "--width", str(W), "--height", str(H),
+                                           "--samples", str(spp), "--bounces", str(depth), "--threads", "8"], cwd=tmp)
+            a, b = out.decode().split(",")
+            out_ms.append(float(a))
+            e2e.append(float(b))
+    ms = statistics.median(out_ms)
+    return {"render_ms": round(ms, 3), "render_ms_min": round(min(out_ms), 3), "e2e_ms": round(statistics.median(e2e), 3),
+            "runs": runs, "value": round(W * H * spp / ms / 1e3, 3)}
+
+
+def reference_gpu_kernels(full):
+    """The reference's own kernels rebuilt -O3 for sm_100 (oracle/_ref), timed by their own render_ms stdout field, --threads 8:
+    GlobalFloat at config 2 (median of 3, SURVEY 8d comparator (ii)) and, when `full`, once at the headline config 4 and
+    GlobalDouble at config 3; the constant- and texture-memory variants at config 2 as timing comparators only."""
     scene, W, H, spp, depth = WORKLOADS["cfg2"]
-
-    def run(exe_name):
-        exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
-        if not os.path.exists(exe):
-            return None
-        runs = []
-        with tempfile.TemporaryDirectory() as tmp:
-            for _ in range(2):
-                out = subprocess.check_output([exe, "--scene_id", str(scene), "--width", str(W), "--height", str(H),
-                                               "--samples", str(spp), "--bounces", str(depth), "--threads", "8"], cwd=tmp)
-                runs.append(float(out.decode().split(",")[0]))
-        ms = min(runs)
-        return {"render_ms": round(ms, 3), "value": round(W * H * spp / ms / 1e3, 3)}
-
-    g = run("global-float-cuda-raytrace")
+    g = _run_ref("global-float-cuda-raytrace", scene, W, H, spp, depth, 3)
     if g is None:
         return None
-    line = {"kernel": "GlobalFloat render rebuilt -O3 sm_100, --threads 8", "workload": f"scene {scene}, {W}x{H}, {spp} spp, {depth} bounces",
-            "render_ms": g["render_ms"], "value": g["value"], "unit": METRIC}
-    for key, exe_name in (("const_float", "const-float-cuda-raytrace"), ("tex_float", "tex-float-cuda-raytrace")):
+    line = {"kernel": "GlobalFloat render rebuilt -O3 sm_100, --threads 8", "unit": METRIC,
+            "cfg2": dict(g, workload=workload_name("cfg2"))}
+    line.update({"workload": workload_name("cfg2"), "render_ms": g["render_ms"], "value": g["value"]})
+    extra = [("const_float", "const-float-cuda-raytrace", "cfg2", 1), ("tex_float", "tex-float-cuda-raytrace", "cfg2", 1)]
+    if full:
+        extra += [("cfg4", "global-float-cuda-raytrace", "cfg4", 1), ("cfg3a_double", "global-double-cuda-raytrace", "cfg3a", 1),
+                  ("cfg3b_double", "global-double-cuda-raytrace", "cfg3b", 1), ("cfg3a", "global-float-cuda-raytrace", "cfg3a", 1),
+                  ("cfg3b", "global-float-cuda-raytrace", "cfg3b", 1)]
+    for key, exe_name, wl, runs in extra:
         try:
-            v = run(exe_name)
+            v = _run_ref(exe_name, *WORKLOADS[wl], runs)
         except Exception as e:                                    # a comparator that fails must not take the bench line with it
             v = {"error": str(e)[:120]}
         if v is not None:
-            line[key] = v
+            line[key] = dict(v, workload=workload_name(wl))
     return line
+
+
+def cli_contract():
+    """The drop-in binary's own stdout contract (`render_ms,e2e_ms`, GF main.cu:342-343,397-398) at the headline config, PPM
+    write included (8.3 M text lines): one run, default options."""
+    exe = os.path.join(ROOT, "raytracingincuda_b200", "bin", "b200-raytrace")
+    scene, W, H, spp, depth = WORKLOADS["cfg4"]
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        out = subprocess.check_output([exe, "--scene_id", str(scene), "--width", str(W), "--height", str(H), "--samples", str(spp),
+                                       "--bounces", str(depth), "--threads", "8"], cwd=tmp)
+        wall = time.perf_counter() - t0
+        ppm = [f for f in os.listdir(tmp) if f.endswith(".ppm")]
+        size = os.path.getsize(os.path.join(tmp, ppm[0])) if ppm else 0
+    a, b = out.decode().split(",")
+    return {"workload": workload_name("cfg4"), "render_ms": round(float(a), 3), "e2e_ms": round(float(b), 3),
+            "process_wall_ms": round(wall * 1e3, 1), "ppm_bytes": size,
+            "note": "e2e_ms: scene build + upload + render + D2H + P3 PPM write, CUDA context creation excluded (GF main.cu:81-95,394-400)"}
 
 
 # ------------------------------------------------------------------ B200 arm ----------------
@@ -261,8 +296,31 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def run_b200_arm(args):
+def fp32_peak(peaks):
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    return SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
 
+
+def lib_id():
+    """Short hash of the library the numbers come from (ncu captures under profiles/ carry the same id)."""
+    import hashlib
+    import raytracingincuda_b200.api as api
+    with open(api.LIB_PATH, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:12]
+
+
+def work_of(st, accel_name, n_slots, ms, peak):
+    """Executed and reference-equivalent FP32 work of one trace launch from the kernel's own counters (rt_stats)."""
+    executed = st.filter_tests * FLOP_PER_FILTER + st.sphere_tests * FLOP_PER_TEST + st.node_visits * FLOP_PER_NODE.get(accel_name, 0)
+    ref_equiv = st.segments * n_slots * FLOP_PER_TEST
+    sec = ms * 1e-3
+    return {"executed_tflops": round(executed / sec / 1e12, 3), "frac_executed": round(executed / sec / 1e12 / peak, 4),
+            "reference_equivalent_tflops": round(ref_equiv / sec / 1e12, 3),
+            "filter_tests": int(st.filter_tests), "exact_sphere_tests": int(st.sphere_tests), "node_visits": int(st.node_visits),
+            "segments": int(st.segments), "binned_segments": int(st.binned_segments)}
+
+
+def run_b200_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -279,219 +337,274 @@ def run_b200_arm(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    extras = not (args.no_extras or args.no_lbvh_extra)
+    peaks, peaks_src = measured_peaks()
+    peak = fp32_peak(peaks)
+    ACCEL = {"auto": api.ACCEL_AUTO, "linear": api.ACCEL_LINEAR, "lbvh": api.ACCEL_LBVH, "grid": api.ACCEL_GRID}
 
-    scene_id, W, H, spp, depth = WORKLOADS[args.workload]
-    grid_accel = args.accel == "grid"
-    lbvh = (scene_id < 0 or args.accel == "lbvh") and not grid_accel
-    accel = api.ACCEL_GRID if grid_accel else (api.ACCEL_LBVH if lbvh else api.ACCEL_LINEAR)
-    slots = rt.scene_scaled(-scene_id) if scene_id < 0 else rt.scene(scene_id)
-    cam = rt.camera(W, H, spp, depth)
-    chunks = rt.num_chunks(W, H, spp)
     r = rt.Renderer(local_rank)
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
-    r.upload_scene(slots)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    frame_dev = torch.empty((H, W, 3), dtype=torch.float32, device=device) if rank == 0 else None
-    trace_ms, launches, segs, tests, nodes, binned = [], [0], [0], [0], [0], [0]
+    def scene_of(scene_id, double=False):
+        return rt.scene_scaled(-scene_id) if scene_id < 0 else rt.scene(scene_id, double=double)
 
-    def note_stats():
-        st = r.stats()
-        trace_ms.append(st.trace_ms)
-        launches[0] += st.launches
-        segs[0], tests[0], nodes[0], binned[0] = st.segments, st.sphere_tests, st.node_visits, st.binned_segments
-        return st
+    # ------------------------------------------------------------------ one workload on this world -----------------
+    class Job:
+        """A workload bound to the renderer: device-resident steps for either partitioning."""
 
-    def step_device():
-        """One render with everything resident on the device; result on rank 0's HBM."""
-        if world == 1:
-            r.render(cam, api.make_opts(accel=accel), out=frame_dev)
-            note_stats()
-            return frame_dev
-        if args.split == "rows":
-            def render_rows(buf):
-                r.render(cam, api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows, accel=accel), out=buf)
-                note_stats()
-            return rtdist.render_rows_split(render_rows, W, H, args.tile_rows, rank, world, device, out=frame_dev)
+        def __init__(self, name, accel="auto", double=False):
+            self.name, self.accel_name, self.double = name, accel, double
+            self.scene_id, self.W, self.H, self.spp, self.depth = WORKLOADS[name]
+            self.slots = scene_of(self.scene_id, double)
+            self.cam = rt.camera(self.W, self.H, self.spp, self.depth, double=double)
+            self.dtype = torch.float64 if double else torch.float32
+            self.frame = torch.empty((self.H, self.W, 3), dtype=self.dtype, device=device) if rank == 0 else None
+            self.acc = None
+            self.trace_ms, self.launches, self.st = [], 0, None
+            self.paths = self.W * self.H * self.spp
 
-        def render_partials(planes, c0, c1):
-            r.render_partials(cam, api.make_opts(split=api.SPLIT_SPP, rank=rank, world=world, accel=accel), planes)
-            note_stats()
-        return rtdist.render_spp_split(render_partials, lambda planes: r.finalize(cam, planes, planes.shape[0], out=frame_dev),
-                                       W, H, chunks, rank, world, device, combine=args.spp_combine)
+        def upload(self):
+            r.upload_scene(self.slots)
 
-    frame_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+        def note(self):
+            self.st = r.stats()
+            self.trace_ms.append(self.st.trace_ms)
+            self.launches += self.st.launches
 
+        def opts(self, **kw):
+            return api.make_opts(accel=ACCEL[self.accel_name], **kw)
+
+        def step(self, split="rows", out=None):
+            out = self.frame if out is None else out
+            if world == 1:
+                r.render(self.cam, self.opts(), out=out)
+                self.note()
+                return out
+            if split == "rows":
+                def render_rows(buf):
+                    r.render(self.cam, self.opts(split=api.SPLIT_ROWS, rank=rank, world=world, tile_rows=args.tile_rows), out=buf)
+                    self.note()
+                return rtdist.render_rows_split(render_rows, self.W, self.H, args.tile_rows, rank, world, device, out=out)
+
+            def render_partials(acc, s0, s1):
+                r.render_partials(self.cam, self.opts(split=api.SPLIT_SPP, rank=rank, world=world), acc)
+                self.note()
+            if self.acc is None:
+                self.acc = torch.empty((self.H, self.W, 3), dtype=torch.int64, device=device)
+
+            def fin(acc):
+                r.finalize(self.cam, acc, out=out)
+                self.launches += 1
+                return out
+            return rtdist.render_spp_split(render_partials, fin, self.W, self.H, self.spp, rank, world, device, acc=self.acc)
+
+        def timed(self, steps, warmup, split="rows"):
+            """(ms per step over all ranks, per-rank trace ms, stats of the last launch) -- CUDA events, max over ranks."""
+            for _ in range(warmup):
+                self.step(split)
+            barrier()
+            self.trace_ms.clear()
+            self.launches = 0
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(steps):
+                self.step(split)
+            ev1.record(stream)
+            barrier()
+            ms = ev0.elapsed_time(ev1) / steps
+            mine = sum(self.trace_ms) / max(1, len(self.trace_ms))
+            t = torch.tensor([ms, mine], dtype=torch.float64, device=device)
+            per_rank = [round(mine, 3)]
+            counters = torch.tensor([self.st.segments, self.st.sphere_tests, self.st.node_visits, self.st.binned_segments,
+                                     self.st.filter_tests, self.st.paths], dtype=torch.int64, device=device)
+            if world > 1:
+                allr = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+                dist.all_gather(allr, t[1:2].clone())
+                per_rank = [round(float(x.item()), 3) for x in allr]
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+            return float(t[0]), float(t[1]), per_rank, [int(x) for x in counters.tolist()]
+
+    def summary(job, ms, kernel_ms, counters):
+        """value + executed-work roofline of one measured workload (whole job, all ranks)."""
+        seg, exact, nodes, binned, filt, paths = counters
+        used = api.ACCEL_NAMES.get(job.st.accel_used, "?")
+        executed = filt * FLOP_PER_FILTER + exact * FLOP_PER_TEST + nodes * FLOP_PER_NODE.get(used, 0)
+        ach = executed / (kernel_ms * 1e-3) / 1e12 / world
+        return {"workload": workload_name(job.name), "dtype": "f64" if job.double else "f32", "accel": used,
+                "value": round(job.paths / (ms * 1e-3) / 1e6, 3), "unit": METRIC, "ms_per_step": round(ms, 3),
+                "kernel_ms": round(kernel_ms, 3), "segments_per_path": round(seg / max(1, paths), 4),
+                "executed_tflops_per_gpu": round(ach, 3), "frac_executed": round(ach / peak, 4),
+                "exact_tests_per_segment": round(exact / max(1, seg), 3), "filter_tests_per_segment": round(filt / max(1, seg), 2),
+                "node_visits_per_segment": round(nodes / max(1, seg), 3), "binned_segments_per_path": round(binned / max(1, paths), 4),
+                "slots": len(job.slots), "regs": job.st.regs, "grid": job.st.grid}
+
+    # ------------------------------------------------------------------ headline -----------------------------------
+    job = Job(args.workload, args.accel)
+    job.upload()
+    frame_host = torch.empty((job.H, job.W, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+    with ClockSampler(local_rank) as clocks:
+        ms, kernel_ms, per_rank_ms, counters = job.timed(args.steps, args.warmup, args.split)
+    timed_launches = job.launches
+    head = summary(job, ms, kernel_ms, counters)
+    build_ms = {"bvh_build_ms": round(job.st.bvh_build_ms, 3), "grid_build_ms": round(job.st.grid_build_ms, 3)}
+
+    # ---- end to end through the C ABI with host buffers: scene slots from host memory in, frame in pinned host memory out ----
     def step_e2e():
-        """Public-API step with host buffers: scene slots from host memory in, frame in pinned
-        host memory out (rank 0)."""
-        r.upload_scene(slots)
+        r.upload_scene(job.slots)
         if world == 1:
-            r.render(cam, api.make_opts(accel=accel), out=frame_host)
-            note_stats()
+            r.render(job.cam, job.opts(), out=frame_host)
             return
-        out = step_device()
+        out = job.step(args.split)
         if rank == 0:
             frame_host.copy_(out, non_blocking=True)
             torch.cuda.synchronize()
-
-    # ---- warm-up ----
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-
-    # ---- timed: device-resident ----
-    trace_ms.clear()
-    launches[0] = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_device()
-        ev1.record(stream)
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    timed_launches = launches[0]
-    step_trace_ms = sum(trace_ms) / max(1, len(trace_ms))
-    segments = segs[0]
-
-    # ---- timed: end to end through the C ABI with host buffers ----
     step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     barrier()
-    e2e_s = time.perf_counter() - t0
-
-    t = torch.tensor([ms, e2e_s * 1e3, step_trace_ms], dtype=torch.float64, device=device)
-    seg_t = torch.tensor([segments, tests[0], nodes[0], binned[0]], dtype=torch.int64, device=device)
-    per_rank_ms = [step_trace_ms]
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=device)
     if world > 1:
-        # every rank's own path-tracing time per step: the step ends with the slowest rank
-        mine = torch.tensor([step_trace_ms], dtype=torch.float64, device=device)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank_ms = [round(float(x.item()), 3) for x in allr]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(seg_t, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, step_trace_ms = [float(x) for x in t.tolist()]
-    segments, sphere_tests, node_visits, binned_segments = [int(x) for x in seg_t.tolist()]
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e[0])
 
     line = None
     if rank == 0:
-        peaks, peaks_src = measured_peaks()
-        paths = W * H * spp
-        ms_per_step = ms / args.steps
-        value = paths / (ms_per_step * 1e-3) / 1e6
-        e2e_value = paths / (e2e_ms / args.steps * 1e-3) / 1e6
-        n_slots = len(slots)
         clk = clocks.summary()
-        # linear scan: segments x slots tests; LBVH: the leaf/big tests the traversal actually made
-        # (grid: the reference's algorithmic work as for the linear scan; the counted tests go into the note)
-        flop = (segments * n_slots if grid_accel else sphere_tests) * FLOP_PER_TEST      # whole job, one step
-        achieved = flop / (step_trace_ms * 1e-3) / 1e12 / world         # per GPU (per launch of the trace kernel)
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
         obs = clk["sm_mhz"] or sm_max
-        if lbvh:
-            # LBVH: FP32 work actually asked for = 2 inflated slab tests per node visit (~52 FLOP: 18 sub/abs for the
-            # distance bound and the slabs, 9 mul/fma, 4 for the inflation, 21 min/max/compare counted as 1 each) plus
-            # 18 FLOP per exact sphere test.  The kernel is issue bound at 14-16 of 32 lanes active (ncu), not DRAM bound.
-            flop_b = node_visits * 52 + sphere_tests * FLOP_PER_TEST
-            ach = flop_b / (step_trace_ms * 1e-3) / 1e12 / world
-            pk = SM_COUNT * FP32_LANES * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-            roof = {"bound": "fp32", "kernel": "trace_kernel<float,lbvh>", "unit": "TFLOP/s", "achieved": round(ach, 3),
-                    "peak": round(pk, 2), "frac": round(ach / pk, 4),
-                    "algorithmic": f"{node_visits} node visits x 52 FLOP + {sphere_tests} exact sphere tests x 18 FLOP per step",
-                    "note": "divergent traversal: issue slots ~80 % busy with 14-16 of 32 lanes active; node records (64 B each, "
-                            "6.4 MB for 99 860 slots) are L1/L2 resident",
-                    "kernel_ms": round(step_trace_ms, 3), "traffic": None}
-        line = {
-            "metric": METRIC, "value": round(value, 3), "unit": METRIC, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload),
-                       "implementation": "float, " + ("uniform grid over the ground plane (EXPERIMENTAL, RT_ENABLE_GRID=1), camera rays "
-                                                           "through per-tile candidate lists" if grid_accel else
-                                                           "on-GPU LBVH" if lbvh else "linear scan in shared memory, camera rays "
-                                                           "through per-tile candidate lists (rt_opts.primary_bins)"),
-                       "l2": "inputs regenerate per step; "
-                                   f"partial planes {chunks}x{W}x{H}x16 B exceed L2", "split": (args.split + ("/" + (args.spp_combine if args.split == "spp" else "nccl-gather"))) if world > 1 else "none",
-                       "chunks": chunks, "seed": 1227},
-            "render_ms": round(ms_per_step, 3),
-            "e2e": {"value": round(e2e_value, 3), "unit": METRIC, "h2d_bytes_per_step": int(slots.nbytes),
-                    "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
-            "gpu_launches": timed_launches,
-            "clocks": clk,
-            "roofline": roof if lbvh else {"bound": "fp32", "kernel": "trace_kernel_pb<float,grid>" if grid_accel else "trace_kernel_pb<float>", "achieved": round(achieved, 3),
-                         "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                         "frac_at_observed_clock": round(achieved / (peak * obs / sm_max), 4),
-                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks_src} MEASURED_PEAKS.json)",
-                         "algorithmic": (f"{sphere_tests} sphere tests x {FLOP_PER_TEST} FLOP per step ({node_visits} BVH node "
-                                         f"visits not counted)" if lbvh else
-                                         f"{segments} segments x {n_slots} slots x {FLOP_PER_TEST} FLOP per step"),
-                         "note": ("achieved counts the reference's arithmetic (18 FLOP per (ray, slot) test of every segment, SURVEY 8d); "
-                                  f"the kernel resolves the {binned_segments} camera-ray segments against per-tile candidate lists "
-                                  f"and scans the other {segments - binned_segments} with a 7-FMA conservative filter per test plus "
-                                  "the exact test on the ~0.5 % candidates"),
-                         "scanned_fraction": round((segments - binned_segments) / max(1, segments), 4),
-                         **({"grid": {"cells_per_segment": round(node_visits / max(1, segments), 3),
-                                      "exact_tests_per_segment": round(sphere_tests / max(1, segments), 3)}} if grid_accel else {}),
-                         "kernel_ms": round(step_trace_ms, 3), "traffic": None},
-        }
-        # DRAM bytes per trace_kernel launch from the committed ncu pass over this same command
-        # (profiles/r01e_bench_kernel_traffic.json); None for workloads that were not captured
+        used = head["accel"]
+        kernel_name = {"linear": "trace_kernel_pb<float,linear>", "lbvh": "trace_kernel_pb<float,lbvh>", "grid": "trace_kernel_pb<float,grid>"}.get(used, used)
+        acc_bytes = job.W * job.H * 24
+        roof = {"bound": "fp32", "kernel": kernel_name, "unit": "TFLOP/s",
+                "achieved": head["executed_tflops_per_gpu"], "peak": round(peak, 2), "frac": head["frac_executed"],
+                "frac_at_observed_clock": round(head["executed_tflops_per_gpu"] / (peak * obs / sm_max), 4),
+                "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks_src} MEASURED_PEAKS.json)",
+                "algorithmic": (f"EXECUTED FP32 work per step from the kernel's counters: {counters[4]} filter tests x {FLOP_PER_FILTER} + "
+                                f"{counters[1]} exact sphere tests x {FLOP_PER_TEST} + {counters[2]} node/cell visits x "
+                                f"{FLOP_PER_NODE.get(used, 0)} FLOP"),
+                "reference_equivalent_tflops": round(counters[0] * head["slots"] * FLOP_PER_TEST / (kernel_ms * 1e-3) / 1e12 / world, 3),
+                "reference_equivalent_note": "SURVEY 8d formula (segments x slots x 18 FLOP): the reference's work, not this kernel's; "
+                                             "it exceeds the peak as soon as an algorithm culls tests, so it is not a roofline fraction",
+                "kernel_ms": round(kernel_ms, 3),
+                "note": ("the traversal kernels (grid / LBVH) are bound by divergence and dependent-load latency, not by the FP32 pipe; the "
+                         "FP32-bound kernel of this path is the shared-memory linear scan: see `linear_scan`") if used != "linear" else
+                        "FP32 issue bound: 7 FFMA2 + LDS.128 + 2 FSETP + 2 predicated OR per record of two tests",
+                "traffic": None}
+        # HBM traffic per trace launch: from the committed ncu pass of THIS library build when there is one, else what the
+        # launch is known to move (accumulators zeroed, read-modify-written band by band through L2, read by finalize)
+        roof["traffic_algorithmic"] = int(acc_bytes * 3 + job.W * job.H * 12)
+        roof["traffic_algorithmic_note"] = (f"{job.W}x{job.H} pixels x (24 B accumulators: zeroed + written back once + read by finalize_kernel) + 12 B frame "
+                                            "store; the round-1 build moved 32 partial planes = 8.5 GB per frame")
         try:
-            with open(os.path.join(ROOT, "profiles", "r01e_bench_kernel_traffic.json")) as f:
-                cap = json.load(f).get(args.workload, {})
-            k = next(v for name, v in cap.items() if "trace_kernel" in name)
-            if world == 1 and not lbvh:
-                line["roofline"]["traffic"] = int(k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"])
-                line["roofline"]["traffic_note"] = ("ncu dram__bytes_read+write per launch; algorithmic HBM bytes are the "
-                                                    f"{chunks}x{W}x{H}x16 B partial planes written once = {chunks * W * H * 16} B")
+            with open(os.path.join(ROOT, "profiles", "r02_bench_kernel_traffic.json")) as f:
+                cap = json.load(f)
+            if cap.get("lib_id") == lib_id():
+                k = cap.get(args.workload, {}).get(kernel_name)
+                if k and world == 1:
+                    roof["traffic"] = int(k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"])
+                    roof["traffic_source"] = "profiles/r02_bench_kernel_traffic.json (ncu dram__bytes_read+write per launch, same library build)"
         except Exception:
             pass
-        st = r.stats()
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": METRIC, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload),
+                       "implementation": f"float, rt_opts_default (accel {args.accel} -> {used}), camera rays through per-tile candidate lists, "
+                                         "64-bit fixed-point accumulation with integer atomics",
+                       "l2": f"inputs regenerate per step; the accumulators ({acc_bytes} B) and the frame exceed L2 at 4K and are rewritten every step",
+                       "split": (args.split + ("/nccl-int64-reduce" if args.split == "spp" else "/nccl-gather")) if world > 1 else "none",
+                       "jobs_per_pixel": job.st.chunks, "seed": 1227, "lib_id": lib_id()},
+            "render_ms": head["ms_per_step"],
+            "e2e": {"value": round(job.paths / (e2e_ms * 1e-3) / 1e6, 3), "unit": METRIC, "h2d_bytes_per_step": int(job.slots.nbytes),
+                    "d2h_bytes_per_step": int(job.W * job.H * 3 * 4), "ms_per_step": round(e2e_ms, 3)},
+            "gpu_launches": timed_launches,
+            "clocks": clk,
+            "roofline": roof,
+            "kernel": dict({k: head[k] for k in ("accel", "regs", "grid", "segments_per_path", "binned_segments_per_path",
+                                                 "exact_tests_per_segment", "filter_tests_per_segment", "node_visits_per_segment")},
+                           block=job.st.block, smem_bytes=job.st.smem_bytes, **build_ms),
+        }
         if world > 1:
             line["per_rank_kernel_ms"] = per_rank_ms
-        line["kernel"] = {"grid": st.grid, "block": st.block, "regs": st.regs, "smem_bytes": st.smem_bytes,
-                          "segments_per_path": round(segments / paths, 4),
-                          "binned_segments_per_path": round(binned_segments / paths, 4)}
-        if world == 1 and not lbvh and not args.no_lbvh_extra:
-            # the same workload with every segment through the shared-memory scan (rt_opts.primary_bins off): same image
-            oo = api.make_opts(primary_bins=api.PBINS_OFF)
-            r.render(cam, oo, out=frame_dev)
-            r.render(cam, oo, out=frame_dev)
-            so = r.stats()
-            line["scan_every_segment"] = {"value": round(paths / (so.render_ms * 1e-3) / 1e6, 3), "unit": METRIC,
-                                          "ms_per_step": round(so.render_ms, 3), "kernel": "trace_kernel<float,linear>",
-                                          "roofline_frac": round(so.segments * n_slots * FLOP_PER_TEST / (so.trace_ms * 1e-3) / 1e12 / peak, 4)}
-        if world == 1 and not lbvh and n_slots >= 256 and not args.no_lbvh_extra:
-            # the same workload through the on-GPU LBVH (bit-identical image): informative, not the headline
-            ob = api.make_opts(accel=api.ACCEL_LBVH)
-            r.render(cam, ob, out=frame_dev)
-            t_l = []
-            for _ in range(2):
-                r.render(cam, ob, out=frame_dev)
-                t_l.append(r.stats().render_ms)
-            sb = r.stats()
-            line["accel_lbvh"] = {"value": round(paths / (min(t_l) * 1e-3) / 1e6, 3), "unit": METRIC,
-                                  "ms_per_step": round(min(t_l), 3), "node_visits_per_segment": round(sb.node_visits / sb.segments, 2),
-                                  "sphere_tests_per_segment": round(sb.sphere_tests / sb.segments, 2)}
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(depth)
-        if world == 1 and not args.no_ref_gpu:
+
+    # ------------------------------------------------------------------ extras (all ranks walk the same sequence) ---
+    if extras and world > 1:
+        splits = {}
+        for sp in ("rows", "spp"):
+            if sp == args.split:
+                if rank == 0:
+                    splits[sp] = {"value": head["value"], "ms_per_step": head["ms_per_step"], "per_rank_kernel_ms": per_rank_ms, "headline": True}
+                continue
+            m, km, pr, _ = job.timed(max(2, min(5, args.steps)), 1, sp)
+            if rank == 0:
+                splits[sp] = {"value": round(job.paths / (m * 1e-3) / 1e6, 3), "ms_per_step": round(m, 3), "per_rank_kernel_ms": pr,
+                              "exchange": "one NCCL sum-reduce of the int64 accumulation buffer (W*H*24 B per rank), bit-identical to 1 GPU"
+                              if sp == "spp" else "NCCL gather of each rank's finished rows"}
+        if rank == 0:
+            line["splits"] = splits
+        if args.workload == "cfg4":
+            j5 = Job("cfg5", "auto")
+            j5.upload()
+            m, km, pr, c5 = j5.timed(2, 1, "rows")
+            if rank == 0:
+                line["cfg5"] = dict(summary(j5, m, km, c5), per_rank_kernel_ms=pr, bvh_build_ms=round(j5.st.bvh_build_ms, 3), split="rows")
+            job.upload()
+    if extras and world == 1 and rank == 0:
+        def quick(name, accel="auto", double=False, reps=2, warm=1):
+            j = Job(name, accel, double)
+            j.upload()
+            m, km, _, c = j.timed(reps, warm)
+            d = summary(j, m, km, c)
+            d["bvh_build_ms"], d["grid_build_ms"] = round(j.st.bvh_build_ms, 3), round(j.st.grid_build_ms, 3)
+            return d
+        # the FP32-bound kernel of this path on the headline workload: the roofline exhibit
+        lin = quick(args.workload, "linear") if head["accel"] != "linear" or args.accel != "linear" else dict(head)
+        lin["roofline"] = {"bound": "fp32", "kernel": "trace_kernel_pb<float,linear>", "unit": "TFLOP/s", "achieved": lin["executed_tflops_per_gpu"],
+                           "peak": round(peak, 2), "frac": lin["frac_executed"],
+                           "reference_equivalent_tflops": round(lin["segments_per_path"] * job.paths * lin["slots"] * FLOP_PER_TEST
+                                                                / (lin["kernel_ms"] * 1e-3) / 1e12, 3),
+                           "ncu": "profiles/r02_pb_linear_key_metrics.csv (sm__pipe_fma_cycles_active, issue slots, of this library build when lib_id matches)"}
+        line["linear_scan"] = lin
+        if len(job.slots) >= 256:
+            line["accel_lbvh"] = quick(args.workload, "lbvh")
+            if head["accel"] != "grid":
+                try:
+                    line["accel_grid"] = quick(args.workload, "grid")
+                except Exception as e:
+                    line["accel_grid"] = {"error": str(e)[:100]}
+        if args.workload == "cfg4":
+            cfgs = {}
+            for key, name, dbl in (("cfg2", "cfg2", False), ("cfg3_scene2", "cfg3a", False), ("cfg3_scene3", "cfg3b", False),
+                                   ("cfg3_scene2_double", "cfg3a", True), ("cfg3_scene3_double", "cfg3b", True), ("cfg5", "cfg5", False)):
+                try:
+                    cfgs[key] = quick(name, "auto", dbl, reps=3)
+                except Exception as e:
+                    cfgs[key] = {"error": str(e)[:100]}
+            line["configs"] = cfgs
+        job.upload()
+    if world == 1 and rank == 0:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(job.depth)
+        if not args.no_ref_gpu:
             try:
-                line["reference_gpu_kernel"] = reference_gpu_kernel()
+                line["reference_gpu_kernel"] = reference_gpu_kernels(full=extras and args.workload == "cfg4")
             except Exception as e:  # the comparator is informative, never fatal
                 line["reference_gpu_kernel"] = {"error": str(e)[:200]}
+            if extras and args.workload == "cfg4":
+                try:
+                    line["cli"] = cli_contract()
+                except Exception as e:
+                    line["cli"] = {"error": str(e)[:200]}
     r.close()
     if world > 1:
         dist.destroy_process_group()

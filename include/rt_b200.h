@@ -226,6 +226,14 @@ int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t 
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
 
+/* Diagnostics: the CHECKED build of the library (librt_b200_checked.so, compiled with -DRT_CHECKS=1) carries a bounds
+ * assertion at every indexed access of its kernels (accumulators, tile lists, candidate words, scene slots, BVH nodes and
+ * stack, grid cells, job decode).  This call synchronises the context's stream, reports how many assertions failed since
+ * the last call (*failures) and the code of the first (*first_code, see RT_CHECK in csrc/), and resets both.
+ * *enabled is 0 -- and nothing else is reported -- in the production build.  selftest != 0 first launches a kernel that
+ * violates one assertion (code 999) on purpose. */
+int rt_debug_checks(rt_ctx *ctx, int32_t *enabled, uint32_t *first_code, uint32_t *failures, int selftest);
+
 /* Diagnostics: audit of the conservative pre-filter the float linear scan runs ahead of the reference's
  * exact discriminant (GF hittable.h:41-47).  n_rays synthetic rays (camera rays, bounce-like rays and rays
  * grazing sphere silhouettes within a few ulp) are tested against every filtered slot both ways.

@@ -199,7 +199,7 @@ int orc_num_chunks(int width, int height, int spp) {
     int64_t npix = (int64_t)width * height;
     int64_t c = ((int64_t)spp + 31) / 32;
     if (npix > 0) {
-        int64_t want = (((int64_t)1 << 20) + npix - 1) / npix;
+        int64_t want = (((int64_t)1 << 28) + npix - 1) / npix;
         if (want > c) c = want;
     }
     if (c > spp) c = spp;

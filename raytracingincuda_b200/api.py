@@ -95,6 +95,7 @@ SYMBOLS = {
     "rt_scene_read_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
     "rt_scene_write_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
     "rt_get_stats": (C.c_int, [_P, _P]),
+    "rt_debug_checks": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "rt_frame_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "rt_frame_free": (C.c_int, [_P, _P]),
     "rt_frame_read": (C.c_int, [_P, _P, _P, C.c_size_t]),
@@ -333,6 +334,12 @@ class Renderer:
         out = (C.c_uint64 * 5)()
         _ck(lib().rt_filter_audit(self._ctx, C.byref(cam), seed, n_rays, out), "rt_filter_audit")
         return dict(zip(("pairs", "exact_pass", "filter_pass", "missed", "skipped"), [int(v) for v in out]))
+
+    def debug_checks(self, selftest=False):
+        """rt_debug_checks: (enabled, first_code, failures) of the checked build's bounds assertions; resets them."""
+        en, code, n = C.c_int32(0), C.c_uint32(0), C.c_uint32(0)
+        _ck(lib().rt_debug_checks(self._ctx, C.byref(en), C.byref(code), C.byref(n), 1 if selftest else 0), "rt_debug_checks")
+        return bool(en.value), code.value, n.value
 
     def stats(self):
         s = Stats()

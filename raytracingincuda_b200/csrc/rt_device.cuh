@@ -13,6 +13,21 @@
 namespace rt {
 
 // ------------------------------------------------------------------------------------------
+// Bounds checks of the CHECKED build (librt_b200_checked.so, -DRT_CHECKS=1).  compute-sanitizer is closed on the GPU pool
+// this was developed on, so the memcheck role is played by assertions of our own at every indexed access of the kernels
+// (accumulators, tile lists, candidate words, scene slots, BVH nodes and stack, grid cells, job decode); a violation is
+// counted in g_rt_check[0] and its code kept in g_rt_check[1] (rt_debug_checks reads and resets them), the access is still
+// made.  The production build compiles the macro away: its SASS is unaffected.
+#ifdef RT_CHECKS
+__device__ unsigned int g_rt_check[2];
+#define RT_CHECK(cond, code)                                                              \
+    do {                                                                                  \
+        if (!(cond)) { if (atomicAdd(&rt::g_rt_check[0], 1u) == 0u) rt::g_rt_check[1] = (unsigned)(code); } \
+    } while (0)
+#else
+#define RT_CHECK(cond, code) do { } while (0)
+#endif
+
 template <typename T> struct Num;
 
 template <> struct Num<float> {
@@ -437,6 +452,7 @@ __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, co
 template <typename T>
 __device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const Vec3<T> &o, const Vec3<T> &d, T a, Hit<T> &hit) {
     using N = Num<T>;
+    RT_CHECK(id >= 0, 101);
     const typename N::vec4 s = lds_geom<T>(geom_addr + (uint32_t)id * (uint32_t)sizeof(typename N::vec4));
     const T ocx = N::sub(s.x, o.x), ocy = N::sub(s.y, o.y), ocz = N::sub(s.z, o.z);
     const T h = N::fma(ocz, d.z, N::fma(ocx, d.x, N::mul(ocy, d.y)));
@@ -556,6 +572,7 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
 #pragma unroll 1
         for (; blk < PAIR_CHUNK && k0 + RT_PAIR_UNROLL <= g.half_pad; ++blk, k0 += RT_PAIR_UNROLL, addr += RT_PAIR_UNROLL * 16u) {
             uint32_t s_own = 0, s_nb = 0;
+            RT_CHECK(blk < PAIR_CHUNK && k0 + RT_PAIR_UNROLL <= g.half_pad && addr + RT_PAIR_UNROLL * 16u <= g.filt_addr + 2u * (uint32_t)g.half_pad * 16u, 104);
 #pragma unroll
             for (int k = 0; k < RT_PAIR_UNROLL; ++k)
                 filter_pair(lds_geom<float>(addr + (uint32_t)k * 16u), r, 1u << k, 0x10000u << k, s_own, s_nb);
@@ -597,6 +614,7 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
                 }
                 const int k = __ffs(w) - 1;
                 w &= w - 1u;
+                RT_CHECK(base + k < n && k < RT_PAIR_UNROLL, 102);                   // padding records (nk = -inf) never pass the filter
                 resolve_slot<T>(g.addr, base + k, o, d, a, hit);
                 ++cnt.exact;
             }
@@ -609,6 +627,7 @@ __device__ __forceinline__ Hit<T> closest_hit_paired(const ScanGeom &g, int n, c
         for (int k = 0; k < g.n_far; ++k) {
             int id;
             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(id) : "r"(g.far_addr + (uint32_t)k * 4u));
+            RT_CHECK(id >= 0 && id < n, 103);
             resolve_slot<T>(g.addr, id, o, d, a, hit);
         }
         cnt.exact += (unsigned)g.n_far;

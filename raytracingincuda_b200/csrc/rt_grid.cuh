@@ -25,6 +25,8 @@ struct GridView {
     const float4 *big_geom;       // spheres outside the grid: tested for every ray
     const int *big_slot;
     int nbig;
+    unsigned int n_items;         // entries of items[]
+    int n_slots;                  // slots of the scene
     int nu, nw;
     int au, av, aw;               // axis numbers of the grid's u, of the slab, of the grid's w
     float lo[3], hi[3];           // bounds of the grid spheres (centre -/+ radius), rounded outwards, in x y z order
@@ -105,9 +107,12 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
         for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
             for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {
                 const int cell = b * g.nu + c;
+                RT_CHECK(cell >= 0 && cell < g.nu * g.nw, 601);
                 const unsigned int e0 = __ldg(g.start + cell), e1 = __ldg(g.start + cell + 1);
+                RT_CHECK(e0 <= e1 && e1 <= g.n_items, 602);
                 for (unsigned int e = e0; e < e1; ++e) {
                     const int slot = (int)__ldg(g.items + e);
+                    RT_CHECK(slot >= 0 && slot < g.n_slots, 603);
                     bvh_test_sphere(__ldg(geom + slot), slot, o, d, a, hit);
                 }
                 n_tests += e1 - e0;

@@ -317,15 +317,17 @@ void rt_opts_default(rt_opts *opts) {
     opts->kernel = RT_KERNEL_MEGA;
 }
 
-// Sample ranges per pixel (scheduling only, see the header).  Jobs of about 32 samples: a launch ends when its last job
-// ends, and long jobs leave the machine draining (125-sample jobs cost a fixed 27 ms per launch at config 4, 32-sample jobs
-// 10 ms); small frames get more, shorter jobs so that there are at least 2^20 of them when spp allows.
+// Sample ranges per pixel (scheduling only, see the header).  A launch ends when its last job ends, so long jobs leave the
+// machine draining: at config 4, 125-sample jobs cost a fixed 27 ms per launch and 32-sample jobs 10 ms; at config 2 -- a
+// 50-80 ms launch -- 25-sample jobs cost 3-9 % against 1-sample jobs (tools/tune_plan.py, profiles/logs/r02c_tune_plan.log).
+// The job fetch is one warp-aggregated atomic and a handful of multiply-highs, so short jobs are cheap: at most 32 samples
+// per job, and shorter ones until the frame has 2^28 jobs (config 4: 32 ranges of 31-32 samples; config 2: one sample per job).
 int rt_num_chunks(int width, int height, int spp) {
     if (spp < 1) return 1;
     const int64_t npix = static_cast<int64_t>(width) * height;
     int64_t c = (static_cast<int64_t>(spp) + 31) / 32;
     if (npix > 0) {
-        const int64_t want = ((int64_t(1) << 20) + npix - 1) / npix;
+        const int64_t want = ((int64_t(1) << 28) + npix - 1) / npix;
         if (want > c) c = want;
     }
     if (c > spp) c = spp;

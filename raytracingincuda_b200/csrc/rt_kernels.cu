@@ -70,7 +70,7 @@ template <typename T> struct TraceArgs {
     SceneBlob scene;
     PhiloxKeys keys;                   // Philox round keys of the seed
     int max_depth;
-    int width;
+    int width, height;
     int tile_rows, rank, world;        // local row -> global row (world == 1: identity)
     JobPlan plan;
     long long *acc;                    // [pix_local][3] fixed-point radiance sums (rt_device.cuh: accumulate)
@@ -80,7 +80,7 @@ template <typename T> struct TraceArgs {
     int bvh_steps;                     // at most this many node visits per loop turn ...
     int bvh_min_active;                // ... and the round ends once fewer lanes than this are still traversing
     const unsigned int *bins;          // trace_kernel_pb only: per-tile candidate lists of the camera rays (rt_primary_bins.cuh)
-    int tiles_x;
+    int tiles_x, tiles;
     int pb_rounds, pb_min;             // camera-ray rounds per loop turn; rounds after the first need this many fresh lanes
 };
 
@@ -185,6 +185,7 @@ __device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
 template <typename T>
 __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hit, Philox &ph, PathState<T> &ps) {
     using N = Num<T>;
+    RT_CHECK(hit.id >= 0 && hit.id < sc.n, 302);
     const typename N::vec4 s = sc.geom[hit.id];
     const typename N::vec4 m = sc.matl[hit.id];
     const int type = sc.type[hit.id];
@@ -293,6 +294,9 @@ __device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned lo
     const int c = (int)cl, C = P.chunks[reg], q = P.spp_q[reg], rem = P.spp_r[reg];
     J.sample = P.s_begin + c * q + (int)((unsigned)(c * rem) / (unsigned)C);
     J.sample_end = P.s_begin + (c + 1) * q + (int)((unsigned)((c + 1) * rem) / (unsigned)C);
+    RT_CHECK(job < P.total_jobs && lp < P.pix_local && cl < (unsigned long long)C && r - cl * bp < bp, 201);
+    RT_CHECK(J.pi >= 0 && J.pi < A.width && J.pj >= 0 && J.pj < A.height, 202);
+    RT_CHECK(J.sample >= P.s_begin && J.sample < J.sample_end && J.sample_end <= P.s_begin + P.s_count, 203);
     return J;
 }
 
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? RT_TRACE_MIN_BLO
     // a path ended with radiance (cr,cg,cb): add it to the pixel's accumulators (GF camera.h:160), move to the next
     // sample of the job or ask for the next job
     auto end_path = [&](T cr, T cg, T cb) {
+        RT_CHECK(local < A.plan.pix_local && state == ACTIVE, 301);
         accumulate<T>(A.acc, local, cr, cg, cb);
         ++n_path;
         if (++sample == sample_end) state = NEED_JOB;
@@ -1036,41 +1041,49 @@ int build_grid(rt_ctx *ctx) {
     }
     double r_med = 0.0;
     if (!rad.empty()) { std::sort(rad.begin(), rad.end()); r_med = rad.size() % 2 ? rad[rad.size() / 2] : 0.5 * (rad[rad.size() / 2 - 1] + rad[rad.size() / 2]); }
+    // Field spheres (radius within a factor 4 of the median) go into the grid; everything else -- the ground, the reference's
+    // three unit spheres, the never-written zero-radius slot, non-finite records -- is tested for every ray.  (Registering the
+    // unit spheres in the cells they overlap was tried: the slab the walk is clipped to grows from 0.4 to 2 units, and the
+    // CPU model visits 2-4x the cells per segment -- more than the three exact tests it saves.)
     std::vector<int> in_grid, big;
     for (int i = 0; i < n; ++i) {
         const float4 &s = g[(size_t)i];
         const double r = std::fabs((double)s.w);
         const bool fin = std::isfinite(s.x) && std::isfinite(s.y) && std::isfinite(s.z) && std::isfinite(r);
-        ((fin && r > 0.0 && r >= 0.25 * r_med && r <= 4.0 * r_med) ? in_grid : big).push_back(i);
+        if (fin && r > 0.0 && r >= 0.25 * r_med && r <= 4.0 * r_med) in_grid.push_back(i);
+        else big.push_back(i);
     }
-    if (!(in_grid.size() >= 2 && big.size() <= 64)) {                // not a field of similar spheres
+    if (in_grid.size() < 2 || big.size() > 64) {                      // not a field of similar spheres
         ctx->grid_ready = true;
         ctx->grid_usable = ctx->grid_auto = false;
         return RT_OK;
     }
     const auto t_build0 = std::chrono::steady_clock::now();
-    struct Undo {                                                     // a failed upload leaves no half-built grid behind
-        rt_ctx *c; bool armed = true;
-        ~Undo() { if (armed) { for (void *&m : c->grid_mem) if (m) { cudaFree(m); m = nullptr; } c->grid = GridView{}; } }
-    } undo{ctx};
     double cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     double lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
     double r_max = 0.0, r_min = INFINITY;
+    auto grow = [&](int i) {
+        const float4 &s = g[(size_t)i];
+        const double c[3] = {s.x, s.y, s.z}, r = std::fabs((double)s.w);
+        for (int q = 0; q < 3; ++q) { lo3[q] = std::min(lo3[q], c[q] - r); hi3[q] = std::max(hi3[q], c[q] + r); }
+    };
     for (int i : in_grid) {
         const float4 &s = g[(size_t)i];
         const double c[3] = {s.x, s.y, s.z}, r = std::fabs((double)s.w);
-        for (int q = 0; q < 3; ++q) {
-            cmin[q] = std::min(cmin[q], c[q]); cmax[q] = std::max(cmax[q], c[q]);
-            lo3[q] = std::min(lo3[q], c[q] - r); hi3[q] = std::max(hi3[q], c[q] + r);
-        }
+        for (int q = 0; q < 3; ++q) { cmin[q] = std::min(cmin[q], c[q]); cmax[q] = std::max(cmax[q], c[q]); }
+        grow(i);
         r_max = std::max(r_max, r); r_min = std::min(r_min, r);
     }
     int av = 0;
     for (int q = 1; q < 3; ++q) if (cmax[q] - cmin[q] < cmax[av] - cmin[av]) av = q;
     const int au = av == 0 ? 1 : 0, aw = av == 2 ? 1 : 2;
-    const double eu = hi3[au] - lo3[au], ew = hi3[aw] - lo3[aw];
-    double h = std::sqrt(std::max(eu * ew, 1e-30) / (double)in_grid.size());
+    double h = std::sqrt(std::max((hi3[au] - lo3[au]) * (hi3[aw] - lo3[aw]), 1e-30) / (double)in_grid.size());
     h = std::max(h, r_max);
+    struct Undo {                                                     // a failed upload leaves no half-built grid behind
+        rt_ctx *c; bool armed = true;
+        ~Undo() { if (armed) { for (void *&m : c->grid_mem) if (m) { cudaFree(m); m = nullptr; } c->grid = GridView{}; } }
+    } undo{ctx};
+    const double eu = hi3[au] - lo3[au], ew = hi3[aw] - lo3[aw];
     const int nu = (int)std::min(std::max(std::ceil(eu / h), 1.0), 4096.0), nw = (int)std::min(std::max(std::ceil(ew / h), 1.0), 4096.0);
     h = std::max(std::max(eu / nu, ew / nw), h);
     GridView G{};
@@ -1127,6 +1140,8 @@ int build_grid(rt_ctx *ctx) {
     G.big_geom = static_cast<const float4 *>(ctx->grid_mem[2]);
     G.big_slot = static_cast<const int *>(ctx->grid_mem[3]);
     G.nbig = (int)big.size();
+    G.n_items = (unsigned int)items.size();
+    G.n_slots = n;
     ctx->grid = G;
     undo.armed = false;
     ctx->grid_ready = true;
@@ -1205,8 +1220,6 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     if (const char *e = getenv("RT_CHUNKS")) { const int v = atoi(e); if (v > 0) c_a = v < s_count ? v : s_count; }   // tuning knob
     int tail_mult = 4;
     if (const char *e = getenv("RT_TAIL_MULT")) { const int v = atoi(e); if (v > 0) tail_mult = v; }
-    long long c_b = (long long)c_a * tail_mult;
-    if (c_b > s_count) c_b = s_count;
     // bands: as many rows as keep the band's accumulators (24 B per pixel) within 8 MB of L2
     long long band_rows = (8ll << 20) / (24ll * width);
     if (const char *e = getenv("RT_BAND_ROWS")) { const int v = atoi(e); if (v > 0) band_rows = v; }
@@ -1216,19 +1229,24 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     const unsigned long long bands = (P.pix_local + band_pix - 1) / band_pix;
     P.band_pix = (unsigned int)band_pix;
     P.last_pix = (unsigned int)(P.pix_local - (bands - 1) * band_pix);
-    P.chunks[0] = c_a; P.chunks[1] = (int)c_b;
-    for (int r = 0; r < 2; ++r) { P.spp_q[r] = s_count / P.chunks[r]; P.spp_r[r] = s_count % P.chunks[r]; }
-    P.band_jobs = band_pix * (unsigned long long)c_a;
-    P.jobs_a = (bands - 1) * P.band_jobs;
     P.rp_b = (bands - 1) * band_pix;
-    P.total_jobs = P.jobs_a + (unsigned long long)P.last_pix * (unsigned long long)c_b;
+    for (;; c_a = (c_a + 1) / 2) {
+        long long c_b = (long long)c_a * tail_mult;
+        if (c_b > s_count) c_b = s_count;
+        P.chunks[0] = c_a; P.chunks[1] = (int)c_b;
+        P.band_jobs = band_pix * (unsigned long long)c_a;
+        P.jobs_a = (bands - 1) * P.band_jobs;
+        P.total_jobs = P.jobs_a + (unsigned long long)P.last_pix * (unsigned long long)c_b;
+        // multiply-high division is exact while dividend * divisor < 2^64; keep a wide margin.  Gigantic renders get longer jobs.
+        if ((long double)P.total_jobs * (long double)P.band_jobs < 9.0e18L && P.chunks[1] <= 16384) break;
+        if (c_a == 1) return RT_EINVAL;
+    }
+    for (int r = 0; r < 2; ++r) { P.spp_q[r] = s_count / P.chunks[r]; P.spp_r[r] = s_count % P.chunks[r]; }
     auto magic = [](unsigned long long d) { return d > 1 ? ~0ull / d + 1ull : 0ull; };
     P.magic_band_jobs = magic(P.band_jobs);
     P.magic_pix[0] = magic(band_pix);
     P.magic_pix[1] = magic(P.last_pix);
     P.magic_width = magic((unsigned long long)width);
-    // multiply-high division is exact while dividend * divisor < 2^64; keep a wide margin
-    if ((long double)P.total_jobs * (long double)P.band_jobs >= 9.0e18L) return RT_EINVAL;
     *out = P;
     return RT_OK;
 }
@@ -1250,6 +1268,8 @@ int fill_args(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int
     A.keys = philox_keys(o.seed);
     A.max_depth = cam.max_depth;
     A.width = cam.width;
+    A.height = cam.height;
+    A.tiles = 0;
     A.tile_rows = o.tile_rows; A.rank = o.rank;
     A.world = (o.split == RT_SPLIT_ROWS) ? o.world : 1;
     const int rc = plan_jobs(cam.width, rows_local, s_begin, s_count, &A.plan);
@@ -1271,6 +1291,7 @@ int build_bins(rt_ctx *ctx, TraceArgs<T> &A, int width, int height, bool from_bv
     unsigned int *bins = static_cast<unsigned int *>(ctx->bins);
     A.bins = bins;
     A.tiles_x = tiles_x;
+    A.tiles = (int)tiles;
     const unsigned bin_grid = (unsigned)((tiles + 127) / 128);
     if (from_bvh) launch_bins_bvh(A.cam, ctx->bvh, width, height, tiles_x, tiles_y, bins, bin_grid, ctx->stream);
     else bin_kernel<T><<<bin_grid, 128, 0, ctx->stream>>>(A.cam, static_cast<const typename Num<T>::vec4 *>(ctx->blob.base), ctx->blob.n,
@@ -1816,6 +1837,27 @@ int rt_filter_audit(rt_ctx *ctx, const rt_camera *cam, uint64_t seed, uint64_t n
     RT_CUDA(cudaMemcpyAsync(h, ctx->queue, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int q = 0; q < 5; ++q) out[q] = h[q];
+    return RT_OK;
+}
+
+#ifdef RT_CHECKS
+namespace rt { __global__ void check_selftest_kernel() { RT_CHECK(threadIdx.x != 0, 999); } }
+#endif
+int rt_debug_checks(rt_ctx *ctx, int32_t *enabled, uint32_t *first_code, uint32_t *failures, int selftest) {
+    if (!ctx || !enabled || !first_code || !failures) return RT_EINVAL;
+    *enabled = 0; *first_code = 0; *failures = 0;
+#ifdef RT_CHECKS
+    RT_CUDA(cudaSetDevice(ctx->device));
+    if (selftest) { rt::check_selftest_kernel<<<1, 32, 0, ctx->stream>>>(); RT_CUDA(cudaGetLastError()); }
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned int h[2] = {0u, 0u};
+    const unsigned int zero[2] = {0u, 0u};
+    RT_CUDA(cudaMemcpyFromSymbol(h, rt::g_rt_check, sizeof h));
+    RT_CUDA(cudaMemcpyToSymbol(rt::g_rt_check, zero, sizeof zero));
+    *enabled = 1; *failures = h[0]; *first_code = h[1];
+#else
+    (void)selftest;
+#endif
     return RT_OK;
 }
 

@@ -267,6 +267,7 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     const float inf = Num<float>::inf();
     ++n_nodes;
     const int node = tv.node;
+    RT_CHECK(node >= 0 && node < bv.m - 1 && tv.sp >= 0 && tv.sp <= BVH_STACK, 501);
     const float4 q0 = __ldg(bv.nodes + 4 * (size_t)node), q1 = __ldg(bv.nodes + 4 * (size_t)node + 1);
     const float4 q2 = __ldg(bv.nodes + 4 * (size_t)node + 2), q3 = __ldg(bv.nodes + 4 * (size_t)node + 3);
     const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
@@ -281,6 +282,7 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
     }
     // leaf tests run inline: parking them per lane to run the tests of many lanes together was measured 4 % SLOWER (the
     // closest hit shrinks later, and the flush adds two ballots per step)
+    RT_CHECK((left < 0 ? ~left < bv.m : left < bv.m - 1) && (right < 0 ? ~right < bv.m : right < bv.m - 1), 502);
     if (tl < inf && left < 0) {
         bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, tv.a, tv.hit);
         ++n_tests;

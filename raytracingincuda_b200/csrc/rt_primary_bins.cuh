@@ -249,6 +249,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
         if (++sample == sample_end) state = NEED_JOB;
     };
     auto end_path = [&](T cr, T cg, T cb) {
+        RT_CHECK(local < A.plan.pix_local && state == ACTIVE, 401);
         accumulate<T>(A.acc, local, cr, cg, cb);                     // integer atomics: order independent (rt_device.cuh)
         end_black();
     };
@@ -293,9 +294,11 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                 ph.block(0);
                 camera_ray(A, pi, pj, ph, ps);
                 depth = 0;
+                RT_CHECK(tile < (uint32_t)A.tiles, 402);
                 const uint4 *rec = reinterpret_cast<const uint4 *>(A.bins) + (size_t)tile * (PB_STRIDE / 4);
                 uint4 q = __ldg(rec);
                 const unsigned cnt = q.x;
+                RT_CHECK(cnt == PB_OVERFLOW || cnt <= (unsigned)PB_CAP, 403);
                 const T a = dot3(ps.d, ps.d);
                 const bool sane = a > T(1e-30) && a < T(1e30);        // false for NaN too: such rays take the scan's exact loop
                 if (cnt == PB_OVERFLOW || !sane) {
@@ -309,6 +312,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                         // the record is consumed one word at a time: rotate the 128-bit window, refill every 4 entries
                         if ((e & 3u) == 0u) q = __ldg(rec + (e >> 2));
                         else { q.x = q.y; q.y = q.z; q.z = q.w; }
+                        RT_CHECK(q.x < (unsigned)A.scene.n, 404);
                         if constexpr (LB || GR) bvh_test_sphere(__ldg(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
                         else resolve_slot<T>(geo.addr, (int)q.x, ps.o, ps.d, a, h);
                     }

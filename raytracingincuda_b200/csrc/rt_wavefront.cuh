@@ -47,6 +47,7 @@ __device__ __forceinline__ void wf_store_path(const WfPool &P, int s, const Path
 // a path of slot `s` ended with radiance c: accumulate, advance the job (same as trace_kernel's end_path)
 __device__ __forceinline__ int wf_end_path(const TraceArgs<float> &A, const WfPool &P, int s, float cr, float cg, float cb,
                                            unsigned int &n_path) {
+    RT_CHECK(s >= 0 && s < P.n && P.local[s] < A.plan.pix_local, 701);
     accumulate<float>(A.acc, P.local[s], cr, cg, cb);
     ++n_path;
     const int smp = P.sample[s] + 1;

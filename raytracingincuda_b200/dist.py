@@ -54,14 +54,18 @@ def render_rows_split(render_rows, width, height, tile_rows, rank, world, device
     return frame
 
 
-def render_spp_split(render_partials, finalize, width, height, spp, rank, world, device, group=None):
+def render_spp_split(render_partials, finalize, width, height, spp, rank, world, device, group=None, acc=None):
     """``render_partials(acc, s0, s1)`` overwrites ``acc`` (a contiguous (height, width, 3) int64 tensor on
-    ``device``) with this rank's fixed-point radiance sums over samples [s0, s1); ``finalize(acc)`` turns the
-    summed accumulators into the frame on rank 0.  Returns the frame on rank 0, None elsewhere."""
+    ``device``; pass one to reuse it across frames) with this rank's fixed-point radiance sums over samples
+    [s0, s1); ``finalize(acc)`` turns the summed accumulators into the frame on rank 0.  Returns the frame on
+    rank 0, None elsewhere."""
     s0, s1 = api.partition_samples(spp, rank, world)
-    acc = torch.zeros((height, width, 3), dtype=torch.int64, device=device)
+    if acc is None:
+        acc = torch.empty((height, width, 3), dtype=torch.int64, device=device)
     if s1 > s0:
         render_partials(acc, s0, s1)
+    else:
+        acc.zero_()
     if world > 1:
         dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM, group=group)      # integer sum: exact in any order
     return finalize(acc) if rank == 0 else None

@@ -606,8 +606,12 @@ def test_bench_line_schema():
         assert key in line, key
     assert line["metric"] == "Mpath-samples/s" and line["value"] > 0 and line["gpu_launches"] == 6       # 2 steps x (bin_kernel, trace_kernel_pb, finalize_kernel)
     assert line["e2e"]["h2d_bytes_per_step"] == 488 * 40 and line["e2e"]["d2h_bytes_per_step"] == 320 * 192 * 12
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
-    assert "workload" in line["config"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "reference_equivalent_tflops"} <= set(line["roofline"])
+    assert 0 < line["roofline"]["frac"] < 1                    # executed FP32 work can never exceed the peak
+    assert "workload" in line["config"] and line["kernel"]["accel"] == "grid"      # scene 1 under rt_opts_default
+    lin = line["linear_scan"]                                  # the FP32-bound exhibit on the same workload
+    assert lin["accel"] == "linear" and 0 < lin["roofline"]["frac"] < 1 and lin["filter_tests_per_segment"] > 100
+    assert line["accel_lbvh"]["accel"] == "lbvh" and line["accel_lbvh"]["node_visits_per_segment"] > 1
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
@@ -791,6 +795,77 @@ def test_full_size_frame_spot_check_vs_oracle(renderer, w, h, spp, depth, double
     for k, (i, j) in enumerate(pts):
         want = O.pixel(oslots, ocam, i, j)
         assert np.array_equal(bits(got[k]), bits(want)), (i, j, got[k], want)
+
+
+CHECKED_CHILD = r"""
+import sys, json
+import numpy as np
+import torch
+import raytracingincuda_b200 as rt
+from raytracingincuda_b200 import api
+r = rt.Renderer(0)
+en, code, n = r.debug_checks()
+assert en, "not the checked build"
+report = {}
+def run(label, fn):
+    fn()
+    en, code, n = r.debug_checks()
+    report[label] = [code, n]
+L, B, G, A = api.ACCEL_LINEAR, api.ACCEL_LBVH, api.ACCEL_GRID, api.ACCEL_AUTO
+for sid in (1, 2, 3):
+    r.upload_scene(rt.scene(sid))
+    cam = rt.camera(97, 61, 9, 25)
+    for accel, name in ((L, "linear"), (B, "lbvh"), (G, "grid")):
+        run(f"scene{sid} {name}", lambda: r.render(cam, api.make_opts(accel=accel)))
+        run(f"scene{sid} {name} primary", lambda: r.primary_hits(rt.camera(97, 61), accel=accel))
+    run(f"scene{sid} linear bins off", lambda: r.render(cam, api.make_opts(accel=L, primary_bins=api.PBINS_OFF)))
+    run(f"scene{sid} lbvh bins off", lambda: r.render(cam, api.make_opts(accel=B, primary_bins=api.PBINS_OFF)))
+    run(f"scene{sid} wavefront", lambda: r.render(cam, api.make_opts(accel=L, kernel=api.KERNEL_WAVEFRONT)))
+    for rank in range(3):
+        run(f"scene{sid} rows {rank}/3", lambda: r.render(cam, api.make_opts(split=api.SPLIT_ROWS, rank=rank, world=3, tile_rows=4)))
+    acc = torch.empty((61, 97, 3), dtype=torch.int64, device="cuda:0")
+    for rank in range(2):
+        run(f"scene{sid} spp {rank}/2", lambda: r.render_partials(cam, api.make_opts(split=api.SPLIT_SPP, rank=rank, world=2), acc))
+    run(f"scene{sid} finalize", lambda: r.finalize(cam, acc))
+    r.upload_scene(rt.scene(sid, double=True))
+    run(f"scene{sid} double", lambda: r.render(rt.camera(64, 40, 6, 25, double=True)))
+    run(f"scene{sid} double primary", lambda: r.primary_hits(rt.camera(64, 40, double=True)))
+for half, label in ((24, "2 308 slots"), (158, "99 860 slots")):
+    r.upload_scene(rt.scene_scaled(half))
+    cam = rt.camera(160, 96, 3, 12)
+    for accel, name in ((B, "lbvh"), (G, "grid"), (A, "auto")) + (((L, "linear"),) if half == 24 else ()):
+        run(f"{label} {name}", lambda: r.render(cam, api.make_opts(accel=accel)))
+        run(f"{label} {name} primary", lambda: r.primary_hits(rt.camera(160, 96), accel=accel))
+r.upload_scene(rt.scene(1))
+run("1080p frame, 2 spp", lambda: r.render(rt.camera(1920, 1080, 2, 50), out=torch.empty((1080, 1920, 3), dtype=torch.float32, device="cuda:0")))
+selftest = r.debug_checks(selftest=True)
+print(json.dumps({"report": report, "selftest": list(selftest)}))
+"""
+
+
+def test_checked_build_finds_no_out_of_bounds_access():
+    """compute-sanitizer is closed on this GPU pool (profiles/logs/r02_sanitizer_closed_message.txt), so the memcheck role is
+    played by the CHECKED build of the library (-DRT_CHECKS=1: a bounds assertion at every indexed access of the kernels):
+    every kernel family on every scene kind must finish without one violation, and the assertion machinery must be alive
+    (its self-test violates one assertion on purpose)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "raytracingincuda_b200", "librt_b200_checked.so")
+    assert os.path.exists(lib), "build it with make -C raytracingincuda_b200/csrc"
+    env = dict(os.environ, RT_B200_LIB=lib, PYTHONPATH=root)
+    p = subprocess.run([sys.executable, "-c", CHECKED_CHILD], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    bad = {k: v for k, v in out["report"].items() if v[1] != 0}
+    assert not bad, bad
+    assert len(out["report"]) > 60
+    assert out["selftest"] == [True, 999, 1]
+
+
+def test_production_build_has_no_checks(renderer):
+    assert renderer.debug_checks() == (False, 0, 0)
 
 
 def test_invalid_inputs_fail_loudly(renderer):

@@ -137,11 +137,12 @@ def test_hit_world_edge_cases():
 def test_job_granularity():
     """Sample ranges per pixel are scheduling only (the accumulation is an integer sum): jobs of at most 32 samples, more
     and shorter jobs on small frames, never more ranges than samples."""
-    assert O.num_chunks(3840, 2160, 1000) == 32
-    assert O.num_chunks(1920, 1080, 100) == 4
+    assert O.num_chunks(3840, 2160, 1000) == 33              # 30-31 samples per job
+    assert O.num_chunks(1920, 1080, 100) == 100              # a short launch: one sample per job
     assert O.num_chunks(320, 192, 10) == 10
-    assert O.num_chunks(320, 192, 4096) == 128
-    assert O.num_chunks(3840, 2160, 256) == 8
+    assert O.num_chunks(320, 192, 4096) == 4096
+    assert O.num_chunks(3840, 2160, 256) == 33
+    assert O.num_chunks(7680, 4320, 100000) == 3125
     assert O.num_chunks(320, 192, 5) == 5
     assert O.num_chunks(8, 8, 100000) == 4096
     for spp in (9, 17, 100, 1000):
