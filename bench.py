@@ -508,7 +508,7 @@ def run_b200_arm(args):
             with open(os.path.join(ROOT, "profiles", "r02_bench_kernel_traffic.json")) as f:
                 cap = json.load(f)
             if cap.get("lib_id") == lib_id():
-                k = cap.get(args.workload, {}).get(kernel_name)
+                k = next((v for name, v in cap.get(args.workload, {}).items() if "trace_kernel" in name), None)
                 if k and world == 1:
                     roof["traffic"] = int(k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"])
                     roof["traffic_source"] = "profiles/r02_bench_kernel_traffic.json (ncu dram__bytes_read+write per launch, same library build)"

@@ -90,39 +90,54 @@ template <typename T> struct PathState {
     T puy;                // y of the normalised PRIMARY direction (sky term, GF camera.h:121)
 };
 
-// get_ray (GF camera.h:145-155) with Philox dimension 0 of (pixel, sample).
-// `ph` is opened on (pixel, sample, 0) and already holds block 0.
-template <typename T>
+// get_ray (GF camera.h:145-155) with Philox dimension 0 of (pixel, sample): block 0 = (x jitter, y jitter, first lens
+// candidate), every later block two lens candidates (float; double: one uniform per two words, so block 0 = the jitter and
+// every later block one candidate).
+// `ph` is opened on (pixel, sample, 0).  HAVE0 (what every kernel uses): it already holds block 0, computed by the caller
+// with all lanes converged; HAVE0 = false computes it at the one Philox site of the loop below -- smaller code, but measured
+// 5 % SLOWER in all three trace kernels (profiles/logs/r02i_philox_site_ab.log).
+template <typename T, bool HAVE0 = true>
 __device__ __forceinline__ void camera_ray(const TraceArgs<T> &A, int i, int j, Philox &ph, PathState<T> &ps) {
     using N = Num<T>;
-    T ux, uy;
-    if (N::words_per_uniform == 1) { ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); }
-    else { ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]); }
-    const T px = N::add(static_cast<T>(i), N::sub(ux, T(0.5)));
-    const T py = N::add(static_cast<T>(j), N::sub(uy, T(0.5)));
+    const bool lens = !(A.cam.defocus_angle <= T(0));
     Vec3<T> target;
-    target.x = N::fma(py, A.cam.dv.x, N::fma(px, A.cam.du.x, A.cam.pixel00.x));
-    target.y = N::fma(py, A.cam.dv.y, N::fma(px, A.cam.du.y, A.cam.pixel00.y));
-    target.z = N::fma(py, A.cam.dv.z, N::fma(px, A.cam.du.z, A.cam.pixel00.z));
-    Vec3<T> o = A.cam.center;
-    if (!(A.cam.defocus_angle <= T(0))) {
-        // defocus_disk_sample / random_in_unit_disk (GF camera.h:73-76, vec3.h:109-115)
-        T q0, q1;
-        for (uint32_t k = 0;; ++k) {
-            uint32_t a0, a1, b0 = 0, b1 = 0;
-            if (N::words_per_uniform == 1) {
-                if (k > 0 && (k & 1u)) ph.block((k + 1u) >> 1);
-                const bool lowpair = (k > 0) && (k & 1u);
-                a0 = lowpair ? ph.w[0] : ph.w[2];
-                a1 = lowpair ? ph.w[1] : ph.w[3];
-            } else {
-                ph.block(1u + k);
-                a0 = ph.w[0]; b0 = ph.w[1]; a1 = ph.w[2]; b1 = ph.w[3];
-            }
-            q0 = N::fma(N::uniform(a0, b0), T(2), T(-1));
-            q1 = N::fma(N::uniform(a1, b1), T(2), T(-1));
-            if (N::fma(q1, q1, N::mul(q0, q0)) < T(1)) break;
+    target.x = target.y = target.z = T(0);
+    T q0 = T(0), q1 = T(0);
+    // defocus_disk_sample / random_in_unit_disk (GF camera.h:73-76, vec3.h:109-115): first candidate inside the unit disk
+    for (uint32_t b = 0;; ++b) {
+        if (!HAVE0 || b > 0) ph.block(b);
+        bool done = false;
+        if (b == 0) {
+            T ux, uy;
+            if (N::words_per_uniform == 1) { ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); }
+            else { ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]); }
+            const T px = N::add(static_cast<T>(i), N::sub(ux, T(0.5)));
+            const T py = N::add(static_cast<T>(j), N::sub(uy, T(0.5)));
+            target.x = N::fma(py, A.cam.dv.x, N::fma(px, A.cam.du.x, A.cam.pixel00.x));
+            target.y = N::fma(py, A.cam.dv.y, N::fma(px, A.cam.du.y, A.cam.pixel00.y));
+            target.z = N::fma(py, A.cam.dv.z, N::fma(px, A.cam.du.z, A.cam.pixel00.z));
+            if (!lens) break;
         }
+        if (N::words_per_uniform == 1) {
+            if (b > 0) {                                     // words 0, 1 of blocks 1, 2, ...
+                q0 = N::fma(N::uniform(ph.w[0], 0), T(2), T(-1));
+                q1 = N::fma(N::uniform(ph.w[1], 0), T(2), T(-1));
+                done = N::fma(q1, q1, N::mul(q0, q0)) < T(1);
+            }
+            if (!done) {                                     // words 2, 3 of every block
+                q0 = N::fma(N::uniform(ph.w[2], 0), T(2), T(-1));
+                q1 = N::fma(N::uniform(ph.w[3], 0), T(2), T(-1));
+                done = N::fma(q1, q1, N::mul(q0, q0)) < T(1);
+            }
+        } else if (b > 0) {
+            q0 = N::fma(N::uniform(ph.w[0], ph.w[1]), T(2), T(-1));
+            q1 = N::fma(N::uniform(ph.w[2], ph.w[3]), T(2), T(-1));
+            done = N::fma(q1, q1, N::mul(q0, q0)) < T(1);
+        }
+        if (done) break;
+    }
+    Vec3<T> o = A.cam.center;
+    if (lens) {
         o.x = N::fma(q1, A.cam.disk_v.x, N::fma(q0, A.cam.disk_u.x, A.cam.center.x));
         o.y = N::fma(q1, A.cam.disk_v.y, N::fma(q0, A.cam.disk_u.y, A.cam.center.y));
         o.z = N::fma(q1, A.cam.disk_v.z, N::fma(q0, A.cam.disk_u.z, A.cam.center.z));
@@ -152,37 +167,13 @@ template <> __device__ __forceinline__ void sky<double>(double puy, double &r, d
     b = __dadd_rn(a, t1);
 }
 
-// random_unit_vector (GF vec3.h:117-127), Philox dimension depth+1, one candidate per block
-// (float) or per two blocks (double).  `ph` already holds block 0.
-template <typename T>
-__device__ __forceinline__ Vec3<T> unit_vector_draw(Philox &ph) {
-    using N = Num<T>;
-    Vec3<T> v;
-    for (uint32_t k = 0;; ++k) {
-        T ux, uy, uz;
-        if (N::words_per_uniform == 1) {
-            if (k > 0) ph.block(k);
-            ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
-        } else {
-            if (k > 0) ph.block(2u * k);
-            ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
-            ph.block(2u * k + 1u);
-            uz = N::uniform(ph.w[0], ph.w[1]);
-        }
-        v.x = N::fma(ux, T(2), T(-1)); v.y = N::fma(uy, T(2), T(-1)); v.z = N::fma(uz, T(2), T(-1));
-        const T l2 = dot3(v, v);
-        if (N::unit_min() < l2 && l2 <= T(1)) {
-            const T inv = N::rcp(N::sqrt(l2));
-            v.x = N::mul(inv, v.x); v.y = N::mul(inv, v.y); v.z = N::mul(inv, v.z);
-            return v;
-        }
-    }
-}
-
 // One bounce: hit record (GF hittable.h:58-63) + the material switch of GF camera.h:92-108.
-// `ph` is opened on (pixel, sample, depth+1) and already holds block 0.
+// `ph` is opened on (pixel, sample, depth+1): block 0 feeds the Schlick uniform of a dielectric (word 0; double: words 0, 1)
+// or the first random_unit_vector candidate (GF vec3.h:117-127; one candidate per block -- float -- or per two blocks --
+// double), later blocks the later candidates.  HAVE0 (what every kernel uses): `ph` already holds block 0; otherwise it is
+// computed at the one Philox site of the candidate loop (smaller, but measured 5 % slower).
 // Returns false when the path is absorbed (metal scattered below the surface, GF material.h:58).
-template <typename T>
+template <typename T, bool HAVE0 = true>
 __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hit, Philox &ph, PathState<T> &ps) {
     using N = Num<T>;
     RT_CHECK(hit.id >= 0 && hit.id < sc.n, 302);
@@ -197,6 +188,33 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
     n.x = N::mul(N::sub(p.x, s.x), inv_r); n.y = N::mul(N::sub(p.y, s.y), inv_r); n.z = N::mul(N::sub(p.z, s.z), inv_r);
     const bool front = dot3(d, n) < T(0);
     if (!front) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+
+    // random numbers of this bounce: the Schlick uniform, or the first candidate in the unit ball that passes
+    // unit_min < |v|^2 <= 1, normalised (random_unit_vector, GF vec3.h:117-127)
+    Vec3<T> uv;
+    uv.x = uv.y = uv.z = T(0);
+    T schlick_u = T(0);
+    for (uint32_t k = 0;; ++k) {
+        T ux, uy, uz;
+        if (N::words_per_uniform == 1) {
+            if (!HAVE0 || k > 0) ph.block(k);
+            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], 0); break; }
+            ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
+        } else {
+            if (!HAVE0 || k > 0) ph.block(2u * k);
+            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], ph.w[1]); break; }
+            ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
+            ph.block(2u * k + 1u);
+            uz = N::uniform(ph.w[0], ph.w[1]);
+        }
+        uv.x = N::fma(ux, T(2), T(-1)); uv.y = N::fma(uy, T(2), T(-1)); uv.z = N::fma(uz, T(2), T(-1));
+        const T l2 = dot3(uv, uv);
+        if (N::unit_min() < l2 && l2 <= T(1)) {
+            const T inv = N::rcp(N::sqrt(l2));
+            uv.x = N::mul(inv, uv.x); uv.y = N::mul(inv, uv.y); uv.z = N::mul(inv, uv.z);
+            break;
+        }
+    }
 
     Vec3<T> nd;
     if (type == RT_DIELECTRIC) {
@@ -216,7 +234,7 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
             r0 = N::mul(r0, r0);
             const T x1 = N::sub(T(1), cos_t), x2 = N::mul(x1, x1), x4 = N::mul(x2, x2), x5 = N::mul(x4, x1);
             const T refl = N::fma(N::sub(T(1), r0), x5, r0);
-            reflect = refl > N::uniform(ph.w[0], ph.w[1]);
+            reflect = refl > schlick_u;
         }
         if (reflect) {
             const T k = N::mul(T(2), dot3(ud, n));
@@ -230,7 +248,6 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
             nd.x = N::fma(k, n.x, perp.x); nd.y = N::fma(k, n.y, perp.y); nd.z = N::fma(k, n.z, perp.z);
         }
     } else {
-        const Vec3<T> uv = unit_vector_draw<T>(ph);
         if (type == RT_LAMBERTIAN) {
             // lambertian_scatter (GF material.h:38-49)
             nd.x = N::add(n.x, uv.x); nd.y = N::add(n.y, uv.y); nd.z = N::add(n.z, uv.z);
@@ -310,15 +327,16 @@ __device__ __forceinline__ unsigned long long claim_job(const TraceArgs<T> &A, i
     return base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
 }
 
-// per-warp reduction of the lanes' work counters into the queue words 1..6
+// per-warp reduction of the lanes' work counters into the queue words 1..6: two REDUX per counter (low and high halves, so
+// the 32-lane sum cannot overflow) instead of five 64-bit shuffle rounds -- the kernel's code footprint matters (I-cache)
 __device__ __forceinline__ void flush_counters(unsigned long long *queue, int lane, unsigned n_seg, unsigned n_path, unsigned n_nodes,
                                                unsigned n_exact, unsigned n_binned, unsigned n_filt) {
-    unsigned long long v[6] = {n_seg, n_path, n_nodes, n_exact, n_binned, n_filt};
-#pragma unroll
+    const unsigned v[6] = {n_seg, n_path, n_nodes, n_exact, n_binned, n_filt};
+#pragma unroll 1
     for (int q = 0; q < 6; ++q) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(FULL, v[q], off);
-        if (lane == 0 && v[q]) atomicAdd(queue + 1 + q, v[q]);
+        const unsigned lo = __reduce_add_sync(FULL, v[q] & 0xffffu), hi = __reduce_add_sync(FULL, v[q] >> 16);
+        const unsigned long long sum = (unsigned long long)lo + ((unsigned long long)hi << 16);
+        if (lane == 0 && sum) atomicAdd(queue + 1 + q, sum);
     }
 }
 
@@ -1093,6 +1111,9 @@ int build_grid(rt_ctx *ctx) {
     for (int q = 0; q < 3; ++q) { G.lo[q] = std::nextafter((float)lo3[q], -INFINITY); G.hi[q] = std::nextafter((float)hi3[q], INFINITY); }
     G.rmin = (float)r_min;
     G.pad = (float)(0.05 * (double)G.h);
+    G.half_pad = G.pad * 0.5f;
+    G.ulo = G.lo[au];
+    G.wlo = G.lo[aw];
     const double hh = G.h, ulo = G.lo[au], wlo = G.lo[aw];
     std::vector<unsigned int> count((size_t)nu * nw + 1, 0u);
     auto range = [&](double c, double R, double base, int cells, int &a0, int &a1) {
@@ -1146,15 +1167,17 @@ int build_grid(rt_ctx *ctx) {
     undo.armed = false;
     ctx->grid_ready = true;
     ctx->grid_usable = true;
-    // RT_ACCEL_AUTO picks the grid for a planar, compact field: the slab axis is thin against the cell size, and the float-noise
-    // inflation of a ray that starts within two diagonals of the field stays inside half the registration padding, so no
-    // step looks beyond its own cell (grid_closest_hit: k_global == 0) -- measured 53.8 / 49.3 ms against 57.6 ms through the
-    // LBVH on scene 1 at config 2, but 95 ms against 47 ms on the 99 860-slot field, where far cells need rings.
+    // RT_ACCEL_AUTO picks the grid for a planar field of moderate extent: the slab axis is thin against the cell size, and the
+    // float-noise inflation delta of a sphere half a diagonal away from the ray origin stays within the registration padding,
+    // so that most steps look at their own cell only.  Measured at 1920x1080 (tools/time_accels.py, profiles/logs/
+    // r02e_time_accels.log; grid / LBVH / scan): 40 slots 19.2 / 20.2 / 21.5 ms, 125 slots 25.0 / 25.2 / 29.8, 488 slots
+    // 47.9 / 51.6 / 80.6, 3 604 slots 59.6 / 71.5 / 656, 14 404 slots 45.8 / 58.2, 99 860 slots (far cells need a ring of
+    // neighbours) 44.1 / 42.1 -- the one case left to the LBVH, which is also the structure BASELINE config 5 names.
     double diag2 = 0.0;
     for (int q = 0; q < 3; ++q) diag2 += (hi3[q] - lo3[q]) * (hi3[q] - lo3[q]);
-    const double reach = 2.0 * std::sqrt(diag2);
-    const double delta_far = (std::sqrt((double)BVH_KEPS * reach * reach + r_min * r_min) - r_min) * 1.001 + 1e-7 + 4.8e-7 * 2.0 * reach;
-    ctx->grid_auto = (hi3[av] - lo3[av]) <= 4.0 * (double)G.h && delta_far <= 0.5 * (double)G.pad && std::isfinite(delta_far);
+    const double reach = 0.5 * std::sqrt(diag2);
+    const double delta_half = (std::sqrt((double)BVH_KEPS * reach * reach + r_min * r_min) - r_min) * 1.001 + 1e-7 + 4.8e-7 * 2.0 * reach;
+    ctx->grid_auto = (hi3[av] - lo3[av]) <= 4.0 * (double)G.h && delta_half <= (double)G.pad && std::isfinite(delta_half);
     ctx->grid_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
     return RT_OK;
 }
@@ -1163,7 +1186,7 @@ int build_grid(rt_ctx *ctx) {
 // Float scenes from RT_AUTO_MIN_SLOTS slots up go through the uniform grid when they are a compact field of similar spheres
 // (build_grid: grid_auto) and through the LBVH otherwise; small scenes, double scenes and the wavefront variant keep the
 // shared-memory scan.
-constexpr int RT_AUTO_MIN_SLOTS = 256;
+constexpr int RT_AUTO_MIN_SLOTS = 32;     // measured (tools/time_accels.py): the grid wins from 40 slots up (scene 2: 19.2 / 20.2 / 21.4 ms grid / LBVH / scan)
 int resolve_accel(rt_ctx *ctx, const rt_opts &o) {
     if (o.accel != RT_ACCEL_AUTO) return o.accel;
     if (ctx->scene_prec != 4 || o.kernel != RT_KERNEL_MEGA) return RT_ACCEL_LINEAR;

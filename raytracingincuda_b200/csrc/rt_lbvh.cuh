@@ -221,17 +221,19 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
     tv.a = dot3(d, d);
     tv.hit.t = N::inf();
     tv.hit.id = -1;
-    for (int b = 0; b < bv.nbig; ++b) bvh_test_sphere(__ldg(bv.big_geom + b), __ldg(bv.big_slot + b), o, d, tv.a, tv.hit);
-    n_tests += bv.nbig;
+    // the spheres outside the tree -- and the tree itself when it is a single sphere -- through ONE copy of the exact test
+    // (the traversal kernels are instruction-fetch bound: every inlined copy of the sqrt/div sequences costs I-cache)
+    const int n_direct = bv.nbig + (bv.m == 1 ? 1 : 0);
+#pragma unroll 1
+    for (int b = 0; b < n_direct; ++b) {
+        const bool big = b < bv.nbig;
+        bvh_test_sphere(__ldg(big ? bv.big_geom + b : bv.geom), __ldg(big ? bv.big_slot + b : bv.slot), o, d, tv.a, tv.hit);
+    }
+    n_tests += n_direct;
     tv.node = -1;
     tv.sp = 0;
-    if (bv.m == 0) return;
-    if (bv.m == 1) {
-        bvh_test_sphere(__ldg(bv.geom), __ldg(bv.slot), o, d, tv.a, tv.hit);
-        ++n_tests;
-        return;
-    }
-    tv.inv.x = 1.0f / d.x; tv.inv.y = 1.0f / d.y; tv.inv.z = 1.0f / d.z;
+    if (bv.m <= 1) return;
+    tv.inv.x = __frcp_rn(d.x); tv.inv.y = __frcp_rn(d.y); tv.inv.z = __frcp_rn(d.z);      // == 1.0f / x, the shorter sequence
     tv.node = 0;
     if (RAYD) {
         // One inflation for the whole traversal: the per-box formula evaluated at the farthest corner of the TREE's bounds
@@ -280,18 +282,19 @@ __device__ __forceinline__ void bvh_step(const BvhView &bv, const Vec3<float> &o
         tl = bvh_box_entry(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q3.z, o, tv.inv, limit);
         tr = bvh_box_entry(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.w, o, tv.inv, limit);
     }
-    // leaf tests run inline: parking them per lane to run the tests of many lanes together was measured 4 % SLOWER (the
-    // closest hit shrinks later, and the flush adds two ballots per step)
-    RT_CHECK((left < 0 ? ~left < bv.m : left < bv.m - 1) && (right < 0 ? ~right < bv.m : right < bv.m - 1), 502);
-    if (tl < inf && left < 0) {
-        bvh_test_sphere(__ldg(bv.geom + ~left), __ldg(bv.slot + ~left), o, d, tv.a, tv.hit);
+    // leaf tests run right here (parking them per lane to run the tests of many lanes together was measured 4 % SLOWER: the
+    // closest hit shrinks later, and the flush adds two ballots per step) -- both children through one copy of the test
+    int leaf = -1, leaf2 = -1;
+    if (tl < inf && left < 0) { leaf = ~left; tl = inf; }
+    if (tr < inf && right < 0) { leaf2 = ~right; tr = inf; }
+    if (leaf < 0) { leaf = leaf2; leaf2 = -1; }
+#pragma unroll 1
+    while (leaf >= 0) {
+        RT_CHECK(leaf < bv.m, 503);
+        bvh_test_sphere(__ldg(bv.geom + leaf), __ldg(bv.slot + leaf), o, d, tv.a, tv.hit);
         ++n_tests;
-        tl = inf;
-    }
-    if (tr < inf && right < 0) {
-        bvh_test_sphere(__ldg(bv.geom + ~right), __ldg(bv.slot + ~right), o, d, tv.a, tv.hit);
-        ++n_tests;
-        tr = inf;
+        leaf = leaf2;
+        leaf2 = -1;
     }
     if (tl < inf && tr < inf) {
         const bool left_first = tl <= tr;

@@ -85,7 +85,7 @@ def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth, accel)
     st = renderer.stats()
     assert st.paths == w * h * spp
     assert st.segments == seg
-    assert st.accel_used == (code if accel != "auto" else (api.ACCEL_GRID if len(slots) >= 256 else api.ACCEL_LINEAR))
+    assert st.accel_used == (code if accel != "auto" else api.ACCEL_GRID)      # the reference's scenes are planar fields
     mism = np.argwhere(bits(img) != bits(ref))
     assert len(mism) == 0, f"{len(mism)} differing channels, first {mism[:3]}"
 
@@ -677,6 +677,60 @@ def test_cli_end_to_end(tmp_path):
     assert np.array_equal(got, (256 * x).astype(int).reshape(-1))
 
 
+def test_cli_multi_gpu_splits_write_the_single_gpu_ppm(tmp_path):
+    """`--gpus N --split rows|spp` (P2P and host gather) write the PPM the single-GPU run writes, byte for byte; unknown
+    values of the extension options fail like a malformed cxxopts argument (abort, status 134)."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "raytracingincuda_b200", "bin", "b200-raytrace")
+    common = ["--scene_id", "1", "--width", "100", "--height", "70", "--samples", "10", "--bounces", "12"]
+    p = subprocess.run([exe, *common, "--accel", "bogus"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == -6 or p.returncode == 134, p.returncode            # SIGABRT
+    assert "incorrect_argument_type" in p.stderr
+    for bad in (["--split", "cols"], ["--primary_bins", "maybe"], ["--precision", "half"], ["--seed", "x1"], ["--kernel", "fast"]):
+        assert subprocess.run([exe, *common, *bad], cwd=tmp_path, capture_output=True).returncode in (-6, 134), bad
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    name = "b200_float_scene1_100x70_10samples_12bounces_8threadsPerBlockRow.ppm"
+    one = tmp_path / "one"
+    one.mkdir()
+    assert subprocess.run([exe, *common], cwd=one, capture_output=True).returncode == 0
+    want = (one / name).read_bytes()
+    n = min(torch.cuda.device_count(), 4)
+    for k, extra in enumerate((["--split", "rows"], ["--split", "spp"], ["--split", "rows", "--gather", "host"],
+                               ["--split", "spp", "--gather", "host"], ["--split", "spp", "--accel", "linear"])):
+        d = tmp_path / f"multi{k}"
+        d.mkdir()
+        p = subprocess.run([exe, *common, "--gpus", str(n), *extra, "--stats"], cwd=d, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, (extra, p.stderr[-500:])
+        assert (d / name).read_bytes() == want, extra
+        assert f'"gpus": {n}' in p.stderr and f'"split": "{extra[1]}"' in p.stderr
+
+
+def test_benchmark_driver_writes_the_reference_csv_schema(tmp_path):
+    """tools/benchmark.py: the reference's sweep (global_float_benchmark.sh:25-82) and its averaging step
+    (timing-benchmarks/process.py:16-33) over the drop-in binary -- same CSV header, one row per run, group means."""
+    import csv
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "raytracingincuda_b200", "bin", "b200-raytrace")
+    out = tmp_path / "b200.csv"
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "benchmark.py"), "--exe", exe, "--out", str(out), "--scenes", "1",
+                        "--sizes", "64x40,96x64", "--samples", "4", "--bounces", "5", "--threads", "8,16", "--runs", "2", "--", "--no-ppm"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    rows = list(csv.reader(open(out)))
+    assert rows[0] == ["scene_id", "width", "height", "samples", "bounces", "threads", "run", "render_only_time_ms", "end_to_end_time_ms"]
+    assert len(rows) == 1 + 2 * 2 * 2                             # threads x sizes x runs
+    assert all(float(r[7]) > 0 and float(r[8]) >= float(r[7]) for r in rows[1:])
+    avg = list(csv.reader(open(tmp_path / "b200_avg.csv")))
+    assert avg[0][:6] == ["scene_id", "width", "height", "samples", "bounces", "threads"] and len(avg) == 1 + 4
+    k = [r for r in rows[1:] if r[:6] == avg[1][:6]]
+    assert abs(float(avg[1][6]) - sum(float(r[7]) for r in k) / len(k)) < 1e-3
+
+
 def test_cli_scene_file_round_trip(tmp_path):
     """General scene loader: --dump_scene writes the generated slots, --scene_file renders them back to the same PPM;
     a hand-written three-sphere file renders to the oracle's image."""
@@ -920,11 +974,12 @@ def test_grid_is_refused_for_a_scene_that_is_not_a_field(renderer):
 
 
 def test_auto_picks_grid_lbvh_linear(renderer):
-    """RT_ACCEL_AUTO: the compact planar field of scene 1 -> grid; the 99 860-slot field (far cells need rings) and a 3-D
-    soup -> LBVH; small and double scenes -> linear scan."""
+    """RT_ACCEL_AUTO: the planar fields of the reference's scenes -> grid; the 99 860-slot field (far cells need rings: BASELINE
+    config 5 names the LBVH) and a 3-D soup -> LBVH; tiny and double scenes -> linear scan."""
     cam = rt.camera(32, 20, 1, 4)
-    for slots, want in ((rt.scene(1), api.ACCEL_GRID), (rt.scene(3), api.ACCEL_LINEAR), (rt.scene_scaled(158), api.ACCEL_LBVH),
-                        (rt.scene_scaled(12), api.ACCEL_GRID)):
+    for slots, want in ((rt.scene(1), api.ACCEL_GRID), (rt.scene(3), api.ACCEL_GRID), (rt.scene(2), api.ACCEL_GRID),
+                        (rt.scene(1)[:20].copy(), api.ACCEL_LINEAR), (rt.scene_scaled(158), api.ACCEL_LBVH),
+                        (rt.scene_scaled(12), api.ACCEL_GRID), (rt.scene_scaled(60), api.ACCEL_GRID)):
         renderer.upload_scene(slots)
         renderer.render(cam)
         assert renderer.stats().accel_used == want, (len(slots), renderer.stats().accel_used)

@@ -104,7 +104,7 @@ def test_one_inflation_per_ray_is_exact_too_but_wasteful_on_large_grids():
             res[local] = (np.float32(t).view(np.uint32), s)
             tested[local] += len(used)
         assert res[True] == res[False] and res[True][1] == int(row[7])
-    assert tested[False] > 4 * tested[True], tested
+    assert tested[False] > 2.5 * tested[True], tested
 
 
 def test_far_origins_widen_the_walk():

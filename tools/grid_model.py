@@ -18,7 +18,9 @@ Conservativeness.
     delta = sqrt(rmin^2 + KEPS * D^2) - rmin (rt_lbvh.cuh), D = distance from the origin to the far corner of the grid.
     A ray with delta <= pad / 2 walks the thin line; the point where it enters the ball of radius r + delta lies pad / 2
     inside the registered footprint, far more than the rounding of the walk.  A ray with a larger delta (origin hundreds of
-    units away) also looks at the k = ceil((delta - pad / 2) / h) rings of cells around every cell of the line.
+    units away) also looks at the k = ceil((delta - pad / 2) / h) rings of cells around every cell of the line: the hit
+    point Q lies within r + delta of c per axis, so the registered footprint reaches to within delta - pad of Q, i.e. into a
+    cell at most ceil((delta - pad) / h) cells from Q's; pad / 2 of the padding is kept as margin for the walk's rounding.
   * Termination: the walk stops after a cell whose exit parameter lies beyond the closest hit so far (or beyond the end of
     the clipped range); a sphere with a closer root has that root inside a cell that was already visited.
 """
@@ -103,7 +105,7 @@ def candidates(G, o, d, limit, t_of, local=True):
     root = f32(np.sqrt(f32(f32(KEPS * D2) + f32(G.rmin * G.rmin)))) * f32(1.0 + 2e-7)      # sqrt.approx is within 2 ulp
     delta = f32(f32(f32(root - G.rmin) * f32(1.001)) + f32(1e-7)) + f32(f32(4.8e-7) * f32(omax + max(fx)))
     half_pad = f32(G.pad * f32(0.5))
-    k = 0 if delta <= half_pad else int(np.ceil(float(f32(delta - half_pad)) / float(G.h))) + 1
+    k = 0 if delta <= half_pad else int(np.ceil(float(f32(delta - half_pad)) / float(G.h)))
     infl = f32(delta + f32(1e-6) * f32(omax + max(fx)))
     # clip the ray to the inflated box of the grid spheres
     t0, t1 = f32(0), f32(limit)
@@ -143,7 +145,7 @@ def candidates(G, o, d, limit, t_of, local=True):
             Ds = f32(f32(f32(t_far * length) * f32(1.0001)) + f32(f32(f32(2.0) * G.h) + delta))
             rs = f32(np.sqrt(f32(f32(KEPS * f32(Ds * Ds)) + f32(G.rmin * G.rmin)))) * f32(1.0 + 2e-7)
             ds = f32(f32(f32(rs - G.rmin) * f32(1.001)) + f32(1e-7)) + f32(f32(4.8e-7) * f32(omax + Ds))
-            k = 0 if ds <= half_pad else min(int(np.ceil(float(f32(ds - half_pad)) / float(G.h))) + 1, k_global)
+            k = 0 if ds <= half_pad else min(int(np.ceil(float(f32(ds - half_pad)) / float(G.h))), k_global)
         cu, cw = min(max(iu, 0), G.nu - 1), min(max(iw, 0), G.nw - 1)
         for b in range(max(cw - k, 0), min(cw + k, G.nw - 1) + 1):
             for a in range(max(cu - k, 0), min(cu + k, G.nu - 1) + 1):

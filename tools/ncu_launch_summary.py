@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """Per-kernel summary of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv`
-launch lists.  usage: ncu_launch_summary.py name=launches.csv [name=launches.csv ...] > traffic.json"""
+launch lists.  usage: ncu_launch_summary.py [--lib-id=ID] name=launches.csv [name=launches.csv ...] > traffic.json"""
 import csv
 import json
 import sys
 from collections import defaultdict
 
 out = {}
-for arg in sys.argv[1:]:
+args = sys.argv[1:]
+if args and args[0].startswith("--lib-id="):          # hash of the library the launch lists were taken with (bench.py: lib_id)
+    out["lib_id"] = args.pop(0).split("=", 1)[1]
+for arg in args:
     name, path = arg.split("=", 1)
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0] != "ID"]
     per = defaultdict(lambda: defaultdict(dict))

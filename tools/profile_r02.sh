@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round-2 evidence run on one B200: GPU test suite (incl. the checked build), smoke, ncu launch lists of the bench command and
+# --set full captures of the three trace kernels (reduced configs so the ~40 replays finish).  Every ncu pass follows a plain
+# run of the same command that exited 0.   usage: bash tools/profile_r02.sh [tag]
+set -u
+O=gpurun_out
+T=${1:-r02}
+python -m pytest tests -m gpu -x -q > $O/pytest_$T.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_$T.log; tail -3 $O/pytest_$T.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$T.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke_$T.log
+python tools/time_accels.py 2>&1 | tee $O/${T}_time_accels.log
+FAST="--no-cpu-baseline --no-ref-gpu --no-extras"
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+LIBID=$(python -c "import bench; print(bench.lib_id())")
+for WL in cfg2 cfg4; do
+  STEPS=3; [ $WL = cfg4 ] && STEPS=1
+  for ACC in auto linear; do
+    python bench.py --workload $WL --accel $ACC --steps $STEPS --warmup 1 $FAST > /dev/null 2>&1 && \
+    ncu --metrics $M --clock-control none --csv --log-file $O/${T}_bench_${WL}_${ACC}_launches.csv python bench.py --workload $WL --accel $ACC --steps $STEPS --warmup 1 $FAST > $O/ncu_${T}_${WL}_${ACC}.log 2>&1
+    echo "launch list $WL $ACC rc=$?"
+  done
+done
+python tools/ncu_launch_summary.py --lib-id=$LIBID cfg2=$O/${T}_bench_cfg2_auto_launches.csv cfg4=$O/${T}_bench_cfg4_auto_launches.csv \
+    cfg2_linear=$O/${T}_bench_cfg2_linear_launches.csv cfg4_linear=$O/${T}_bench_cfg4_linear_launches.csv > $O/${T}_bench_kernel_traffic.json
+B=raytracingincuda_b200/bin/b200-raytrace
+CLI="$B --scene_id 1 --width 1920 --height 1080 --samples 16 --bounces 25 --no-ppm --stats"
+for V in "linear:--accel linear" "grid:--accel grid" "lbvh_s1:--accel lbvh" "lbvh_100k:--scaled_half 158"; do
+  NAME=${V%%:*}; FLAGS=${V#*:}
+  $CLI $FLAGS > $O/plain_${T}_$NAME.log 2>&1 && \
+  ncu --set full --import-source on --clock-control none -k regex:trace_kernel_pb -o $O/prof_${T}_pb_$NAME -f $CLI $FLAGS > $O/ncu_${T}_$NAME.log 2>&1
+  echo "ncu $NAME rc=$?"
+done
+cp raytracingincuda_b200/librt_b200.so $O/librt_b200_$T.so        # the cubin the captures ran (tools/ncu_summarise.sh joins it by line)
+ls -la $O/prof_${T}_pb*.ncu-rep
