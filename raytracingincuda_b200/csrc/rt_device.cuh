@@ -449,6 +449,26 @@ __device__ __forceinline__ Hit<T> closest_hit_exact(const ScanGeom &g, int n, co
 //     minimum wins, ties go to the lowest slot: same rule as the LBVH leaves), so own-half, other-half
 //     and far candidates can be resolved in any order.
 // Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // 1 MUFU; within 2 ulp
+    return y;
+}
+
+// Are both roots of a sphere test at or below tmin?  Decided WITHOUT the IEEE square root and divisions, conservatively:
+// true only when the reference's own far root, div.rn(h + sqrt.rn(disc), a), is certainly <= tmin (then the near root is
+// too, and GF hittable.h:49-56 accepts nothing).  This is the commonest test of all -- every scattered ray is tested
+// against the sphere it just left (c ~ 0, h < 0: roots ~ 2h/a and ~ 0) -- and it was paying ~45 instructions of
+// sqrt + 2 divisions to reject.  sqrt.approx is within 2 ulp, so s_hi = approx * (1 + 4e-7) >= sqrt.rn(disc); rounding is
+// monotonic, so fl(h + s_hi) >= fl(h + sqrt.rn(disc)); and x <= tmin * a * (1 - 1e-6) (two roundings of 2^-24 each) implies
+// x / a < tmin, hence div.rn(x, a) <= tmin.  (disc below 1e-30 is left to the exact path: the .ftz approximation flushes
+// subnormal inputs to zero.)
+__device__ __forceinline__ bool roots_below_tmin(float h, float disc, float a) {
+    const float s_hi = sqrt_approx(disc) * 1.0000004f;
+    return disc >= 1e-30f && (h + s_hi) <= (Num<float>::tmin() * a) * 0.999999f;
+}
+__device__ __forceinline__ bool roots_below_tmin(double, double, double) { return false; }
+
 template <typename T>
 __device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const Vec3<T> &o, const Vec3<T> &d, T a, Hit<T> &hit) {
     using N = Num<T>;
@@ -463,6 +483,7 @@ __device__ __forceinline__ void resolve_slot(uint32_t geom_addr, int id, const V
     if (h < T(0) && c > T(0)) return;
     const T disc = N::fma(h, h, -N::mul(a, c));                  // GF hittable.h:41-46
     if (disc < T(0)) return;                                     // GF hittable.h:47 (also drops filter false positives)
+    if (roots_below_tmin(h, disc, a)) return;                    // e.g. the sphere the ray just left
     const T sq = N::sqrt(disc);
     T v = N::div(N::sub(h, sq), a);
     if (!(N::tmin() < v)) {

@@ -149,6 +149,7 @@ __device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const 
     float h;
     const float disc = disc_of<float>(s, o, d, a, h);
     if (disc < 0.0f) return;
+    if (roots_below_tmin(h, disc, a)) return;
     const float sq = N::sqrt(disc);
     float v = N::div(N::sub(h, sq), a);
     if (!(N::tmin() < v)) {
@@ -156,12 +157,6 @@ __device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const 
         if (!(N::tmin() < v)) return;
     }
     if (v < hit.t || (v == hit.t && slot < hit.id)) { hit.t = v; hit.id = slot; }
-}
-
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // 1 MUFU; 2 ulp, covered by the 1.001 factor below
-    return y;
 }
 
 // entry parameter of the inflated box, or +inf when the ray cannot touch it before `limit`.
