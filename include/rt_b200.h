@@ -250,6 +250,8 @@ int rt_frame_free(rt_ctx *ctx, void *dev_ptr);
 int rt_frame_read(rt_ctx *ctx, const void *dev_ptr, void *host_ptr, size_t bytes);
 int rt_frame_write(rt_ctx *ctx, void *dev_ptr, const void *host_ptr, size_t bytes);
 int rt_enable_peer_access(rt_ctx *ctx, int peer_device);     /* 0 also when access was already enabled */
+/* Copy `bytes` from a buffer on another device into a buffer on this context's device (copy engines over NVLink). */
+int rt_copy_peer(rt_ctx *ctx, void *dst_dev, const void *src_peer, int src_device, size_t bytes);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ SYMBOLS = {
     "rt_frame_read": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rt_frame_write": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rt_enable_peer_access": (C.c_int, [_P, C.c_int]),
+    "rt_copy_peer": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t]),
 }
 
 _LIB = None

@@ -1282,7 +1282,10 @@ int fill_args(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int
     A.bvh_min_active = 0;
     A.bins = nullptr;
     A.tiles_x = 0;
-    A.pb_rounds = 3;                   // measured at config 2 (tools/tune_pbins.sh): 1 round 89-91 ms, 2 rounds 87.5-88, 3+ rounds 86.5-87
+    // camera-ray rounds per loop turn.  The shared-memory scan is expensive and must run with full warps: 3 rounds (measured at
+    // config 2: 1 round 89-91 ms, 2 rounds 87.5-88, 3+ rounds 86.5-87); the grid walk and the LBVH traversal are cheap next to
+    // a round: 1 round (36.69 / 36.85 ms grid, 50.01 / 50.22 ms LBVH for 1 / 3 rounds, profiles/logs/r02l_tile_capacity_rounds.log)
+    A.pb_rounds = resolve_accel(ctx, o) == RT_ACCEL_LINEAR ? 3 : 1;
     A.pb_min = 1;
     if (const char *e = getenv("RT_PB_ROUNDS")) A.pb_rounds = atoi(e) > 0 ? atoi(e) : A.pb_rounds;       // tuning knobs
     if (const char *e = getenv("RT_PB_MIN")) A.pb_min = atoi(e);
@@ -1829,6 +1832,13 @@ int rt_frame_write(rt_ctx *ctx, void *dev_ptr, const void *host_ptr, size_t byte
     if (!ctx || !dev_ptr || !host_ptr) return RT_EINVAL;
     RT_CUDA(cudaSetDevice(ctx->device));
     RT_CUDA(cudaMemcpy(dev_ptr, host_ptr, bytes, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+int rt_copy_peer(rt_ctx *ctx, void *dst_dev, const void *src_peer, int src_device, size_t bytes) {
+    if (!ctx || !dst_dev || !src_peer) return RT_EINVAL;
+    RT_CUDA(cudaSetDevice(ctx->device));
+    RT_CUDA(cudaMemcpyPeerAsync(dst_dev, ctx->device, src_peer, src_device, bytes, ctx->stream));
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 int rt_enable_peer_access(rt_ctx *ctx, int peer_device) {

@@ -38,7 +38,10 @@ namespace rt {
 #define RT_PB_SHIFT 4
 #endif
 constexpr int PB_SHIFT = RT_PB_SHIFT;       // tiles of 16 x 16 pixels
-constexpr int PB_STRIDE = 32;               // uint32 per tile record: [0] = count or PB_OVERFLOW, [1..31] = slots
+#ifndef RT_PB_STRIDE
+#define RT_PB_STRIDE 64       // 63 slots per tile: measured against 31 / 127 (profiles/logs/r02l_tile_capacity_rounds.log): 14 404 slots
+#endif                        // 39.9 -> 38.0 ms (binned camera rays 0.935 -> 0.999), scene 1 and the 99 860-slot scene unchanged; 127 slower
+constexpr int PB_STRIDE = RT_PB_STRIDE;     // uint32 per tile record: [0] = count or PB_OVERFLOW, [1..] = slots (a multiple of 4)
 constexpr int PB_CAP = PB_STRIDE - 1;
 constexpr unsigned PB_OVERFLOW = 0xffffffffu;
 constexpr double PB_NOISE = 64.0 * 5.9604644775390625e-08;      // 64 * 2^-24, see above

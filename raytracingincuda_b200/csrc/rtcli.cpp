@@ -113,7 +113,7 @@ Args parse(int argc, char **argv) {
         else if (name == "gpus") a.gpus = to_int(name, value);
         else if (name == "split") { to_choice(value, {{"rows", 0}, {"spp", 1}}); a.split = value; }
         else if (name == "prefix") a.prefix = value;
-        else if (name == "gather") { to_choice(value, {{"p2p", 0}, {"host", 1}}); a.gather = value; }
+        else if (name == "gather") { to_choice(value, {{"p2p", 0}, {"host", 1}, {"p2p-load", 2}}); a.gather = value; }
         else if (name == "scene_file") a.scene_file = value;
         else if (name == "dump_scene") a.dump_scene = value;
         else if (name == "accel")
@@ -265,10 +265,26 @@ int main(int argc, char **argv) {
     for (const auto &d : dev) render_ms = d.render_ms > render_ms ? d.render_ms : render_ms;   // max over devices
     if (spp_split) {
         float fin_ms = 0.f;
-        if (p2p) {
+        if (p2p && a.gather == "p2p-load") {
+            // device 0's finalize kernel reads its peers' buffers directly (P2P loads over NVLink): reduce + gamma + store fused
             std::vector<const int64_t *> list;
             for (void *p : acc) list.push_back(static_cast<const int64_t *>(p));
             CHECK(rt_finalize_sum(dev[0].ctx, &cam, list.data(), a.gpus, frame.data(), &fin_ms));
+        } else if (p2p) {
+            // default: the copy engines bring the peers' buffers to device 0 (posted NVLink writes at full rate), the finalize
+            // kernel adds the local copies
+            const auto t0 = std::chrono::steady_clock::now();
+            std::vector<void *> stage(static_cast<size_t>(a.gpus), nullptr);
+            std::vector<const int64_t *> list{static_cast<const int64_t *>(acc[0])};
+            for (int g = 1; g < a.gpus; ++g) {
+                CHECK(rt_frame_alloc(dev[0].ctx, acc_bytes, &stage[g]));
+                CHECK(rt_copy_peer(dev[0].ctx, stage[g], acc[g], g, acc_bytes));
+                list.push_back(static_cast<const int64_t *>(stage[g]));
+            }
+            const float copy_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            CHECK(rt_finalize_sum(dev[0].ctx, &cam, list.data(), a.gpus, frame.data(), &fin_ms));
+            for (int g = 1; g < a.gpus; ++g) CHECK(rt_frame_free(dev[0].ctx, stage[g]));
+            fin_ms += copy_ms;                                   // the exchange is part of the render time; the D2H of the frame is not
         } else {
             // no peer access: add the accumulators on the host (integers: any order), finalize on device 0
             std::vector<int64_t> total(npix * 3, 0), part(npix * 3);

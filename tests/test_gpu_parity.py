@@ -699,7 +699,8 @@ def test_cli_multi_gpu_splits_write_the_single_gpu_ppm(tmp_path):
     want = (one / name).read_bytes()
     n = min(torch.cuda.device_count(), 4)
     for k, extra in enumerate((["--split", "rows"], ["--split", "spp"], ["--split", "rows", "--gather", "host"],
-                               ["--split", "spp", "--gather", "host"], ["--split", "spp", "--accel", "linear"])):
+                               ["--split", "spp", "--gather", "host"], ["--split", "spp", "--gather", "p2p-load"],
+                               ["--split", "spp", "--accel", "linear"])):
         d = tmp_path / f"multi{k}"
         d.mkdir()
         p = subprocess.run([exe, *common, "--gpus", str(n), *extra, "--stats"], cwd=d, capture_output=True, text=True, timeout=300)

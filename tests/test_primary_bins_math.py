@@ -14,7 +14,7 @@ import pytest
 
 import oracle_lib as O
 
-PB_SHIFT, PB_CAP = 4, 31
+PB_SHIFT, PB_CAP = 4, 63
 PB_NOISE = 64.0 * 2.0 ** -24
 
 
