@@ -28,4 +28,3 @@ for lib in sorted(glob.glob("build/variants/librt_b200_*.so")):
     p = subprocess.run([sys.executable, "-c", CHILD % ROOT], env=env, capture_output=True, text=True)
     print(os.path.basename(lib), p.stdout.strip() or p.stderr[-300:], flush=True)
 PY
-for R in 1 2 3 4; do echo "RT_PB_ROUNDS=$R"; RT_PB_ROUNDS=$R python tools/tune.py --accel grid pb32; RT_PB_ROUNDS=$R python tools/tune.py --accel lbvh pb32; done
