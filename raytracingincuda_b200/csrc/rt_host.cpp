@@ -15,6 +15,7 @@
 #include <limits>
 #include <string>
 #include <type_traits>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -222,28 +223,44 @@ inline char *put_int(char *p, int v) {
     return p;
 }
 
+template <typename T> char *format_pixels(const T *rgb, size_t n, char *p) {
+    for (size_t k = 0; k < n; ++k) {
+        const T *px = rgb + k * 3;
+        p = put_int(p, code_value(px[0])); *p++ = ' ';
+        p = put_int(p, code_value(px[1])); *p++ = ' ';
+        p = put_int(p, code_value(px[2])); *p++ = '\n';
+    }
+    return p;
+}
+
+// Large frames are formatted by several host threads, each into its own buffer, and written in order: the text of a 4K frame is
+// 94 MB, and formatting it is most of what the reference's e2e timer sees after the render (GF main.cu:361-379).
 template <typename T> int write_ppm(const char *path, const T *rgb, int width, int height) {
     if (!path || !rgb || width <= 0 || height <= 0) return RT_EINVAL;
     FILE *f = std::fopen(path, "wb");
     if (!f) return RT_EIO;
     std::fprintf(f, "P3\n%d %d\n255\n", width, height);
     const size_t npix = static_cast<size_t>(width) * height;
-    const size_t batch = 1 << 16;
-    std::vector<char> buf(batch * 12);
-    for (size_t base = 0; base < npix; base += batch) {
-        const size_t n = npix - base < batch ? npix - base : batch;
-        char *p = buf.data();
-        for (size_t k = 0; k < n; ++k) {
-            const T *px = rgb + (base + k) * 3;
-            p = put_int(p, code_value(px[0])); *p++ = ' ';
-            p = put_int(p, code_value(px[1])); *p++ = ' ';
-            p = put_int(p, code_value(px[2])); *p++ = '\n';
-        }
-        if (std::fwrite(buf.data(), 1, static_cast<size_t>(p - buf.data()), f) != static_cast<size_t>(p - buf.data())) {
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t parts = npix < (size_t(1) << 20) ? 1 : (hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+    std::vector<std::vector<char>> buf(parts);
+    std::vector<size_t> used(parts, 0);
+    auto work = [&](size_t k) {
+        const size_t b = npix * k / parts, e = npix * (k + 1) / parts;
+        buf[k].resize((e - b) * 12);
+        used[k] = static_cast<size_t>(format_pixels(rgb + b * 3, e - b, buf[k].data()) - buf[k].data());
+    };
+    if (parts == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < parts; ++k) th.emplace_back(work, k);
+        for (auto &t : th) t.join();
+    }
+    for (size_t k = 0; k < parts; ++k)
+        if (std::fwrite(buf[k].data(), 1, used[k], f) != used[k]) {
             std::fclose(f);
             return RT_EIO;
         }
-    }
     return std::fclose(f) == 0 ? RT_OK : RT_EIO;
 }
 
