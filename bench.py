@@ -304,11 +304,9 @@ def fp32_peak(peaks):
 
 
 def lib_id():
-    """Short hash of the library the numbers come from (ncu captures under profiles/ carry the same id)."""
-    import hashlib
+    """Hash of the device sources the loaded library was built from (ncu captures under profiles/ carry the same id)."""
     import raytracingincuda_b200.api as api
-    with open(api.LIB_PATH, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:12]
+    return api.lib().rt_kernel_build_id().decode()
 
 
 def work_of(st, accel_name, n_slots, ms, peak):

@@ -83,10 +83,11 @@ enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
  * same image, bit for bit; they differ in speed only.
  *   LINEAR  the reference's linear scan, in shared memory (float and double scenes up to 65 535 slots);
  *   LBVH    LBVH built on the device (float scenes of any size);
- *   GRID    uniform grid over the two long axes of a field of similar spheres (float scenes; RT_EINVAL if the scene is not
+ *   GRID    uniform grid over the two long axes of a field of similar spheres (float scenes of any size, double scenes up to
+ *           8 192 slots: the walk runs in float on the rounded ray, the exact tests in double; RT_EINVAL if the scene is not
  *           such a field: fewer than two similar spheres or more than 64 of a very different size);
- *   AUTO    (default) LINEAR below 256 slots, for double scenes and for the wavefront kernel; otherwise GRID when the
- *           scene is a compact planar field of similar spheres (the reference's scenes), else LBVH. */
+ *   AUTO    (default) LINEAR below 32 slots and for the wavefront kernel; otherwise GRID when the scene is a planar field of
+ *           similar spheres of moderate extent (the reference's scenes), else LBVH (float) or LINEAR (double). */
 enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2, RT_ACCEL_GRID = 4 };
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 enum { RT_PBINS_AUTO = 0, RT_PBINS_OFF = 1, RT_PBINS_ON = 2 };   /* AUTO: on wherever it applies */
@@ -175,6 +176,9 @@ int rt_ppm_quantise(const float *rgb, size_t n, uint8_t *out);
 
 const char *rt_error_string(int code);
 int rt_abi_version(void);
+/* Hash of the device sources this library was built from: ties a measurement (bench.py config.lib_id) to the ncu captures and
+ * SASS excerpts under profiles/. */
+const char *rt_kernel_build_id(void);
 
 /* ------------------------------------------------------------------ device side ----------- */
 typedef struct rt_ctx rt_ctx;
@@ -223,6 +227,7 @@ int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double 
 /* Same pass through the chosen acceleration structure (RT_ACCEL_LBVH builds the tree on the device, RT_ACCEL_GRID the grid
  * on the host, on first use); the result is identical to the linear scan's. */
 int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t);
+int rt_primary_hits_accel64(rt_ctx *ctx, const rt_camera64 *cam, int accel, int32_t *ids, double *t);   /* LINEAR, GRID or AUTO */
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats);
 

@@ -65,6 +65,7 @@ class Stats(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     "rt_abi_version": (C.c_int, []),
+    "rt_kernel_build_id": (C.c_char_p, []),
     "rt_scene_generate": (C.c_int, [C.c_int, _P, C.c_int]),
     "rt_scene_generate64": (C.c_int, [C.c_int, _P, C.c_int]),
     "rt_scene_generate_scaled": (C.c_int, [C.c_int, _P, C.c_int]),
@@ -91,6 +92,7 @@ SYMBOLS = {
     "rt_primary_hits": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits64": (C.c_int, [_P, _P, _P, _P]),
     "rt_primary_hits_accel": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "rt_primary_hits_accel64": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "rt_filter_audit": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "rt_scene_read_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
     "rt_scene_write_text": (C.c_int, [C.c_char_p, _P, C.c_int]),
@@ -323,8 +325,8 @@ class Renderer:
         ids = np.empty((cam.height, cam.width), dtype=np.int32)
         t = np.empty((cam.height, cam.width), dtype=np.float64 if double else np.float32)
         if accel != ACCEL_LINEAR:
-            _ck(lib().rt_primary_hits_accel(self._ctx, C.byref(cam), accel, ids.ctypes.data, t.ctypes.data),
-                "rt_primary_hits_accel")
+            fn = lib().rt_primary_hits_accel64 if double else lib().rt_primary_hits_accel
+            _ck(fn(self._ctx, C.byref(cam), accel, ids.ctypes.data, t.ctypes.data), "rt_primary_hits_accel")
             return ids, t
         fn = lib().rt_primary_hits64 if double else lib().rt_primary_hits
         _ck(fn(self._ctx, C.byref(cam), ids.ctypes.data, t.ctypes.data), "rt_primary_hits")

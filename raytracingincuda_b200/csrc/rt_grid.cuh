@@ -39,11 +39,20 @@ struct GridView {
 __constant__ GridView g_grid;     // one grid per device (set by the launch that uses it)
 
 __device__ __forceinline__ float axis_of(const Vec3<float> &v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+__device__ __forceinline__ float4 ldg_geom(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ double4 ldg_geom(const double4 *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+// the closest hit so far as a float that is not below it (the walk's stop test runs in float)
+__device__ __forceinline__ float hit_t_up(float t) { return t; }
+__device__ __forceinline__ float hit_t_up(double t) { return __double2float_ru(t); }
 
 // Cold path of a step whose inflation reaches beyond its own cell (cells hundreds of units from the ray origin): every cell
 // within k rings.  Out of line: the walk's hot loop stays small (the kernel is instruction-fetch bound).
-__device__ __noinline__ void grid_ring_tests(const float4 *__restrict__ geom, int cu, int cw, int k, Vec3<float> o, Vec3<float> d, float a,
-                                             Hit<float> &hit, unsigned &n_tests) {
+template <typename T>
+__device__ __noinline__ void grid_ring_tests(const typename Num<T>::vec4 *__restrict__ geom, int cu, int cw, int k, Vec3<T> o, Vec3<T> d, T a,
+                                             Hit<T> &hit, unsigned &n_tests) {
     const GridView &g = g_grid;
     for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
         for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {
@@ -54,7 +63,7 @@ __device__ __noinline__ void grid_ring_tests(const float4 *__restrict__ geom, in
             for (unsigned int e = e0; e < e1; ++e) {
                 const int slot = (int)__ldg(g.items + e);
                 RT_CHECK(slot >= 0 && slot < g.n_slots, 603);
-                bvh_test_sphere(__ldg(geom + slot), slot, o, d, a, hit);
+                bvh_test_sphere<T>(ldg_geom(geom + slot), slot, o, d, a, hit);
             }
             n_tests += e1 - e0;
         }
@@ -63,14 +72,21 @@ __device__ __noinline__ void grid_ring_tests(const float4 *__restrict__ geom, in
 // closest hit of one ray; `geom` is the scene's geometry by slot (global memory).
 // One loop tests "the current list" -- first the spheres outside the grid, then the cell of every step of the walk -- so the
 // exact sphere test (sqrt and two IEEE divisions inline) exists once in the hot code.
-__device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const float4 *__restrict__ geom, const Vec3<float> &o,
-                                                       const Vec3<float> &d, unsigned &n_cells, unsigned &n_tests) {
-    using N = Num<float>;
-    const float inf = N::inf();
-    Hit<float> hit;
-    hit.t = inf;
+// T = double (a GlobalDouble scene): the walk runs in float on the rounded ray -- rounding moves a point of the ray by ~1e-7
+// relative, four orders below the registration padding, and the double discriminant's own noise is ~1e-16, so the cells the
+// float walk visits list every sphere the double test can accept -- and the exact tests run in double on the double geometry.
+template <typename T>
+__device__ __forceinline__ Hit<T> grid_closest_hit(const GridView &g, const typename Num<T>::vec4 *__restrict__ geom, const Vec3<T> &oT,
+                                                   const Vec3<T> &dT, unsigned &n_cells, unsigned &n_tests) {
+    const float inf = Num<float>::inf();
+    Hit<T> hit;
+    hit.t = Num<T>::inf();
     hit.id = -1;
-    const float a = dot3(d, d);
+    const T aT = dot3(dT, dT);
+    Vec3<float> o, d;
+    o.x = (float)oT.x; o.y = (float)oT.y; o.z = (float)oT.z;
+    d.x = (float)dT.x; d.y = (float)dT.y; d.z = (float)dT.z;
+    const float a = sizeof(T) == 4 ? (float)aT : dot3(d, d);
     // walk state (set up after the first list)
     float t1 = 0.0f, iu_inv = 0.0f, iw_inv = 0.0f, delta = 0.0f;
     int iu = 0, iw = 0, su = 0, sw = 0, k_global = 0, steps_left = -1;        // steps_left < 0: the big list is being tested
@@ -82,7 +98,7 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
         for (; e < e1; ++e) {
             const int slot = (int)__ldg(list + e);
             RT_CHECK(slot >= 0 && slot < g.n_slots, 603);
-            bvh_test_sphere(__ldg(geom + slot), slot, o, d, a, hit);
+            bvh_test_sphere<T>(ldg_geom(geom + slot), slot, oT, dT, aT, hit);
         }
         if (steps_left < 0) {
             // ---- the spheres outside the grid are done: set up the walk ----
@@ -104,7 +120,7 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
             inv.y = d.y != 0.0f ? fminf(fmaxf(__frcp_rn(d.y), -1e30f), 1e30f) : 1e30f;
             inv.z = d.z != 0.0f ? fminf(fmaxf(__frcp_rn(d.z), -1e30f), 1e30f) : 1e30f;
             float t0 = 0.0f;
-            t1 = hit.t;
+            t1 = hit_t_up(hit.t);
             {
                 const float ax = ((g.lo[0] - infl) - o.x) * inv.x, bx = ((g.hi[0] + infl) - o.x) * inv.x;
                 const float ay = ((g.lo[1] - infl) - o.y) * inv.y, by = ((g.hi[1] + infl) - o.y) * inv.y;
@@ -130,7 +146,7 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
             // exit parameters of the current cell, recomputed from the cell index (no accumulated drift)
             const float tu = su == 0 ? inf : ((g.ulo + (float)(iu + (su > 0 ? 1 : 0)) * g.h) - axis_of(o, g.au)) * iu_inv;
             const float tw = sw == 0 ? inf : ((g.wlo + (float)(iw + (sw > 0 ? 1 : 0)) * g.h) - axis_of(o, g.aw)) * iw_inv;
-            const float t_exit = fminf(tu, tw), stop = fminf(hit.t, t1);
+            const float t_exit = fminf(tu, tw), stop = fminf(hit_t_up(hit.t), t1);
             if (!(t_exit <= stop * 1.0001f + 1e-6f) || --steps_left <= 0) break;
             if (tu <= tw) iu += su; else iw += sw;
         }
@@ -153,7 +169,7 @@ __device__ __forceinline__ Hit<float> grid_closest_hit(const GridView &g, const 
             k = ds <= g.half_pad ? 0 : min((int)fminf(ceilf((ds - g.half_pad) / g.h), 8192.0f), k_global);
         }
         if (k > 0) {
-            grid_ring_tests(geom, cu, cw, k, o, d, a, hit, n_tests);
+            grid_ring_tests<T>(geom, cu, cw, k, oT, dT, aT, hit, n_tests);
             e = e1 = 0u;
         } else {
             const int cell = cw * g.nu + cu;

@@ -591,8 +591,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_const
         d.z = N::sub(N::fma(fj, cam.dv.z, N::fma(fi, cam.du.z, cam.pixel00.z)), cam.center.z);
         Hit<T> hit;
         if constexpr (ACCEL == RT_ACCEL_LBVH && sizeof(T) == 4) hit = bvh_closest_hit(bvh, cam.center, d, n_nodes, n_tests);
-        else if constexpr (ACCEL == RT_ACCEL_GRID && sizeof(T) == 4)
-            hit = grid_closest_hit(g_grid, static_cast<const float4 *>(scene.base), cam.center, d, n_nodes, n_tests);
+        else if constexpr (ACCEL == RT_ACCEL_GRID)
+            hit = grid_closest_hit<T>(g_grid, static_cast<const typename Num<T>::vec4 *>(scene.base), cam.center, d, n_nodes, n_tests);
         else hit = closest_hit<T>(geo, scene.n, cam.center, d, cand, TRACE_BLOCK);
         if (valid) {
             ids[k] = hit.id;
@@ -897,12 +897,11 @@ template <typename T, typename Slot> int upload(rt_ctx *ctx, const Slot *slots, 
     for (void *&m : ctx->grid_mem) if (m) { cudaFree(m); m = nullptr; }
     ctx->grid_ready = ctx->grid_usable = ctx->grid_auto = false;
     ctx->grid = GridView{};
-    ctx->host_geom.clear();
-    if (sizeof(T) == 4) {
-        ctx->host_geom.resize((size_t)n);
-        for (int i = 0; i < n; ++i)
-            ctx->host_geom[(size_t)i] = make_float4((float)slots[i].cx, (float)slots[i].cy, (float)slots[i].cz, (float)slots[i].r);
-    }
+    // float copy of the geometry for the host-side builds (LBVH classification: float scenes only; uniform grid: double scenes
+    // too -- the registration padding, 5 % of a cell, covers the rounding by orders of magnitude)
+    ctx->host_geom.resize((size_t)n);
+    for (int i = 0; i < n; ++i)
+        ctx->host_geom[(size_t)i] = make_float4((float)slots[i].cx, (float)slots[i].cy, (float)slots[i].cz, (float)slots[i].r);
     return RT_OK;
 }
 
@@ -1049,7 +1048,7 @@ int build_lbvh(rt_ctx *ctx) {
 // the structure does not fit (fewer than two similar spheres, more than 64 spheres of a very different size).
 int build_grid(rt_ctx *ctx) {
     if (ctx->grid_ready) return RT_OK;
-    if (ctx->scene_prec != 4 || ctx->host_geom.empty()) return RT_EPRECISION;
+    if (ctx->host_geom.empty()) return RT_ENOSCENE;
     const std::vector<float4> &g = ctx->host_geom;
     const int n = (int)g.size();
     std::vector<double> rad;
@@ -1186,16 +1185,19 @@ int build_grid(rt_ctx *ctx) {
 // Float scenes from RT_AUTO_MIN_SLOTS slots up go through the uniform grid when they are a compact field of similar spheres
 // (build_grid: grid_auto) and through the LBVH otherwise; small scenes, double scenes and the wavefront variant keep the
 // shared-memory scan.
+constexpr int GRID_BINS_FROM_BVH = 8192;    // above this the grid's tile lists come from a walk of the LBVH (float scenes only)
 constexpr int RT_AUTO_MIN_SLOTS = 32;     // measured (tools/time_accels.py): the grid wins from 40 slots up (scene 2: 19.2 / 20.2 / 21.4 ms grid / LBVH / scan)
 int resolve_accel(rt_ctx *ctx, const rt_opts &o) {
     if (o.accel != RT_ACCEL_AUTO) return o.accel;
-    if (ctx->scene_prec != 4 || o.kernel != RT_KERNEL_MEGA) return RT_ACCEL_LINEAR;
+    if (o.kernel != RT_KERNEL_MEGA) return RT_ACCEL_LINEAR;
     int min_slots = RT_AUTO_MIN_SLOTS;
     if (const char *e = getenv("RT_AUTO_MIN_SLOTS")) min_slots = atoi(e);                    // tuning knob
     if (ctx->blob.n < min_slots) return RT_ACCEL_LINEAR;
-    if (o.primary_bins != RT_PBINS_OFF && !getenv("RT_AUTO_NO_GRID") && build_grid(ctx) == RT_OK && ctx->grid_usable && ctx->grid_auto)
+    const bool is_double = ctx->scene_prec != 4;
+    if (o.primary_bins != RT_PBINS_OFF && !getenv("RT_AUTO_NO_GRID") && !(is_double && ctx->blob.n > GRID_BINS_FROM_BVH) &&
+        build_grid(ctx) == RT_OK && ctx->grid_usable && ctx->grid_auto)
         return RT_ACCEL_GRID;
-    return RT_ACCEL_LBVH;
+    return is_double ? RT_ACCEL_LINEAR : RT_ACCEL_LBVH;                 // the LBVH is a float structure
 }
 int resolve_accel(rt_ctx *ctx, int accel) {
     rt_opts o;
@@ -1397,50 +1399,44 @@ int trace_wavefront(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_loca
     return WavefrontImpl<T, Cam>::run(ctx, cam, o, rows_local, s_begin, s_count, acc);
 }
 
-// RT_ACCEL_GRID (float): camera rays through the tile lists, scattered rays through the uniform grid.
-template <typename T, typename Cam> struct GridImpl {
-    static int run(rt_ctx *, const Cam &, const rt_opts &, int, int, int, long long *) { return RT_EPRECISION; }
-};
-template <typename T, typename Cam>
-int trace_grid(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
-    return GridImpl<T, Cam>::run(ctx, cam, o, rows_local, s_begin, s_count, acc);
-}
-
 template <typename T, int ACCEL> void launch_pb(const TraceArgs<T> &A, int grid, size_t smem, cudaStream_t st) {
-    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR) trace_kernel_pb<T, ACCEL><<<grid, TRACE_BLOCK, smem, st>>>(A);
+    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR || ACCEL == RT_ACCEL_GRID) trace_kernel_pb<T, ACCEL><<<grid, TRACE_BLOCK, smem, st>>>(A);
 }
 template <typename T, int ACCEL> int shape_pb(rt_ctx *ctx, size_t smem, int *grid) {
-    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR) return launch_shape(ctx, trace_kernel_pb<T, ACCEL>, smem, grid);
+    if constexpr (sizeof(T) == 4 || ACCEL == RT_ACCEL_LINEAR || ACCEL == RT_ACCEL_GRID) return launch_shape(ctx, trace_kernel_pb<T, ACCEL>, smem, grid);
     else return RT_EPRECISION;
 }
 
-template <typename Cam> struct GridImpl<float, Cam> {
-    static int run(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
-        int rc = build_grid(ctx);
-        if (rc) return rc;
-        if (!ctx->grid_usable) return RT_EINVAL;                    // not a field of similar spheres: use RT_ACCEL_LBVH
-        int grid = 0;
-        rc = launch_shape(ctx, trace_kernel_pb<float, RT_ACCEL_GRID>, 0, &grid);
-        if (rc) return rc;
-        TraceArgs<float> A;
-        rc = fill_args<float>(ctx, cam, o, rows_local, s_begin, s_count, acc, A);
-        if (rc) return rc;
-        if (A.plan.total_jobs == 0) return RT_OK;
-        const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
-        if (A.plan.total_jobs < lanes) grid = (int)((A.plan.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
-        ctx->stats.grid = grid;
-        // large scenes: the tile lists come from a walk of the LBVH (one thread per tile cannot loop over 10^5 slots)
-        const bool from_bvh = ctx->blob.n > 8192;
-        if (from_bvh) { rc = build_lbvh(ctx); if (rc) return rc; }
-        rc = build_bins<float>(ctx, A, cam.width, cam.height, from_bvh);
-        if (rc) return rc;
-        RT_CUDA(cudaMemcpyToSymbolAsync(g_grid, &ctx->grid, sizeof(GridView), 0, cudaMemcpyHostToDevice, ctx->stream));
-        trace_kernel_pb<float, RT_ACCEL_GRID><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(A);
-        RT_CUDA(cudaGetLastError());
-        ctx->stats.launches += 1;
-        return RT_OK;
-    }
-};
+// RT_ACCEL_GRID: camera rays through the tile lists, scattered rays through the uniform grid.  Float scenes of any size; double
+// scenes (the walk runs in float on the rounded ray, the exact tests in double) up to 8 192 slots -- above that the tile lists
+// come from a walk of the LBVH, which is a float structure.
+template <typename T, typename Cam>
+int trace_grid(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_begin, int s_count, long long *acc) {
+    const bool from_bvh = ctx->blob.n > GRID_BINS_FROM_BVH;
+    if (from_bvh && sizeof(T) != 4) return RT_EPRECISION;
+    int rc = build_grid(ctx);
+    if (rc) return rc;
+    if (!ctx->grid_usable) return RT_EINVAL;                    // not a field of similar spheres: use RT_ACCEL_LBVH
+    int grid = 0;
+    rc = shape_pb<T, RT_ACCEL_GRID>(ctx, 0, &grid);
+    if (rc) return rc;
+    TraceArgs<T> A;
+    rc = fill_args<T>(ctx, cam, o, rows_local, s_begin, s_count, acc, A);
+    if (rc) return rc;
+    if (A.plan.total_jobs == 0) return RT_OK;
+    const unsigned long long lanes = (unsigned long long)grid * TRACE_BLOCK;
+    if (A.plan.total_jobs < lanes) grid = (int)((A.plan.total_jobs + TRACE_BLOCK - 1) / TRACE_BLOCK);
+    ctx->stats.grid = grid;
+    // large scenes: the tile lists come from a walk of the LBVH (one thread per tile cannot loop over 10^5 slots)
+    if (from_bvh) { rc = build_lbvh(ctx); if (rc) return rc; }
+    rc = build_bins<T>(ctx, A, cam.width, cam.height, from_bvh);
+    if (rc) return rc;
+    RT_CUDA(cudaMemcpyToSymbolAsync(g_grid, &ctx->grid, sizeof(GridView), 0, cudaMemcpyHostToDevice, ctx->stream));
+    launch_pb<T, RT_ACCEL_GRID>(A, grid, 0, ctx->stream);
+    RT_CUDA(cudaGetLastError());
+    ctx->stats.launches += 1;
+    return RT_OK;
+}
 
 // Launches the path tracer for samples [s_begin, s_begin + s_count) of `rows_local` rows into the accumulators `acc`
 // (which the caller has zeroed).
@@ -1602,12 +1598,6 @@ int render_impl(rt_ctx *ctx, const Cam *cam, const rt_opts *opts_in, T *out_rgb,
     return RT_OK;
 }
 
-inline void launch_primary_grid(const DevCamera<float> &cam, const SceneBlob &scene, const BvhView &bvh, int w, int h, int32_t *ids, float *t,
-                                int grid_dim, cudaStream_t st) {
-    primary_kernel<float, RT_ACCEL_GRID><<<grid_dim, TRACE_BLOCK, 0, st>>>(cam, scene, bvh, w, h, ids, t);
-}
-inline void launch_primary_grid(const DevCamera<double> &, const SceneBlob &, const BvhView &, int, int, int32_t *, double *, int, cudaStream_t) {}
-
 template <typename T, typename Cam>
 int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (!ctx || !cam || !ids || !t) return RT_EINVAL;
@@ -1617,7 +1607,7 @@ int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
     if (ctx->scene_prec != (int)sizeof(T)) return RT_EPRECISION;
     accel = resolve_accel(ctx, accel);
     const bool grid = accel == RT_ACCEL_GRID;
-    if ((grid || accel == RT_ACCEL_LBVH) && sizeof(T) != 4) return RT_EPRECISION;
+    if (accel == RT_ACCEL_LBVH && sizeof(T) != 4) return RT_EPRECISION;
     RT_CUDA(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)cam->width * cam->height;
     const bool ids_dev = is_device_ptr(ids), t_dev = is_device_ptr(t);
@@ -1647,7 +1637,8 @@ int primary_impl(rt_ctx *ctx, const Cam *cam, int accel, int32_t *ids, T *t) {
         int grid_dim = (int)((npix + TRACE_BLOCK - 1) / TRACE_BLOCK);
         if (grid_dim > ctx->sm_count * 8) grid_dim = ctx->sm_count * 8;
         if (grid)
-            launch_primary_grid(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width, cam->height, d_ids, d_t, grid_dim, ctx->stream);
+            primary_kernel<T, RT_ACCEL_GRID><<<grid_dim, TRACE_BLOCK, 0, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width,
+                                                                                        cam->height, d_ids, d_t);
         else if (lbvh)
             primary_kernel<T, RT_ACCEL_LBVH><<<grid_dim, TRACE_BLOCK, 0, ctx->stream>>>(to_dev<T>(*cam), ctx->blob, ctx->bvh, cam->width,
                                                                                         cam->height, d_ids, d_t);
@@ -1809,6 +1800,9 @@ int rt_primary_hits64(rt_ctx *ctx, const rt_camera64 *cam, int32_t *ids, double 
 int rt_primary_hits_accel(rt_ctx *ctx, const rt_camera *cam, int accel, int32_t *ids, float *t) {
     return primary_impl<float>(ctx, cam, accel, ids, t);
 }
+int rt_primary_hits_accel64(rt_ctx *ctx, const rt_camera64 *cam, int accel, int32_t *ids, double *t) {
+    return primary_impl<double>(ctx, cam, accel, ids, t);
+}
 
 int rt_frame_alloc(rt_ctx *ctx, size_t bytes, void **dev_ptr) {
     if (!ctx || !dev_ptr || bytes == 0) return RT_EINVAL;
@@ -1893,6 +1887,11 @@ int rt_debug_checks(rt_ctx *ctx, int32_t *enabled, uint32_t *first_code, uint32_
 #endif
     return RT_OK;
 }
+
+#ifndef RT_KERNEL_ID
+#define RT_KERNEL_ID "unknown"
+#endif
+const char *rt_kernel_build_id(void) { return RT_KERNEL_ID; }
 
 int rt_get_stats(rt_ctx *ctx, rt_stats *stats) {
     if (!ctx || !stats) return RT_EINVAL;

@@ -142,21 +142,25 @@ __global__ void bvh_refit_kernel(int m, const int2 *__restrict__ children, const
 }
 
 // ------------------------------------------------------------------------------ traversal ---
-// exact sphere test with the order-independent acceptance rule (see the header comment)
-__device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const Vec3<float> &o, const Vec3<float> &d,
-                                                float a, Hit<float> &hit) {
-    using N = Num<float>;
-    float h;
-    const float disc = disc_of<float>(s, o, d, a, h);
-    if (disc < 0.0f) return;
+// exact sphere test with the order-independent acceptance rule (see the header comment); T = double for the uniform grid over
+// a double scene (GD hittable.h:40-66)
+template <typename T>
+__device__ __forceinline__ void bvh_test_sphere(const typename Num<T>::vec4 s, int slot, const Vec3<T> &o, const Vec3<T> &d, T a, Hit<T> &hit) {
+    using N = Num<T>;
+    T h;
+    const T disc = disc_of<T>(s, o, d, a, h);
+    if (disc < T(0)) return;
     if (roots_below_tmin(h, disc, a)) return;
-    const float sq = N::sqrt(disc);
-    float v = N::div(N::sub(h, sq), a);
+    const T sq = N::sqrt(disc);
+    T v = N::div(N::sub(h, sq), a);
     if (!(N::tmin() < v)) {
         v = N::div(N::add(h, sq), a);
         if (!(N::tmin() < v)) return;
     }
     if (v < hit.t || (v == hit.t && slot < hit.id)) { hit.t = v; hit.id = slot; }
+}
+__device__ __forceinline__ void bvh_test_sphere(const float4 s, int slot, const Vec3<float> &o, const Vec3<float> &d, float a, Hit<float> &hit) {
+    bvh_test_sphere<float>(s, slot, o, d, a, hit);
 }
 
 // entry parameter of the inflated box, or +inf when the ray cannot touch it before `limit`.

@@ -213,7 +213,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     constexpr bool LB = (ACCEL == RT_ACCEL_LBVH || ACCEL == ACCEL_LBVH_COMPACT);
     constexpr bool RAYD = (ACCEL == ACCEL_LBVH_COMPACT);
     constexpr bool GR = (ACCEL == RT_ACCEL_GRID);                  // experimental uniform grid (rt_grid.cuh)
-    static_assert(!(LB || GR) || sizeof(T) == 4, "the LBVH and the grid are float structures");
+    static_assert(!LB || sizeof(T) == 4, "the LBVH is a float structure");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     SceneView<T> sc;
@@ -322,7 +322,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
                         if ((e & 3u) == 0u) q = __ldg(rec + (e >> 2));
                         else { q.x = q.y; q.y = q.z; q.z = q.w; }
                         RT_CHECK(q.x < (unsigned)A.scene.n, 404);
-                        if constexpr (LB || GR) bvh_test_sphere(__ldg(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
+                        if constexpr (LB || GR) bvh_test_sphere<T>(ldg_geom(sc.geom + q.x), (int)q.x, ps.o, ps.d, a, h);
                         else resolve_slot<T>(geo.addr, (int)q.x, ps.o, ps.d, a, h);
                     }
                     s_cnt[3][threadIdx.x] += cnt;
@@ -363,7 +363,7 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
             // a grid walk is short (1.3 cells on average, tools/analyse_accel.py): it runs to the end right here
             if (state == ACTIVE && phase == RAY) {
                 unsigned int n_nodes = 0, n_tests = 0;
-                const Hit<T> h = grid_closest_hit(g_grid, sc.geom, ps.o, ps.d, n_nodes, n_tests);
+                const Hit<T> h = grid_closest_hit<T>(g_grid, sc.geom, ps.o, ps.d, n_nodes, n_tests);
                 s_cnt[2][threadIdx.x] += n_nodes;
                 s_cnt[3][threadIdx.x] += n_tests;
                 land(h);

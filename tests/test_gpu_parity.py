@@ -90,15 +90,34 @@ def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth, accel)
     assert len(mism) == 0, f"{len(mism)} differing channels, first {mism[:3]}"
 
 
+@pytest.mark.parametrize("accel", ["linear", "grid"])
 @pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 32, 20, 6, 25), (2, 48, 32, 9, 50), (3, 40, 24, 8, 50), (1, 21, 13, 40, 50)])
-def test_render_bit_exact_vs_oracle_double(renderer, scene_id, w, h, spp, depth):
-    """GlobalDouble path (GD camera.h:133-177): whole frames bit for bit against the oracle, scenes 1-3."""
+def test_render_bit_exact_vs_oracle_double(renderer, scene_id, w, h, spp, depth, accel):
+    """GlobalDouble path (GD camera.h:133-177): whole frames bit for bit against the oracle, scenes 1-3, through the
+    shared-memory scan and through the uniform grid (float walk on the rounded ray, exact tests in double)."""
     renderer.upload_scene(rt.scene(scene_id, double=True))
     cam = rt.camera(w, h, spp, depth, double=True)
-    img = renderer.render(cam)
+    img = renderer.render(cam, api.make_opts(accel=api.ACCEL_GRID if accel == "grid" else api.ACCEL_LINEAR))
     ref, seg = O.render(O.scene(scene_id, True), O.camera(w, h, spp, depth, double=True))
     assert renderer.stats().segments == seg
     assert np.array_equal(bits(img), bits(ref))
+    ids, t = renderer.primary_hits(rt.camera(97, 61, double=True), accel=api.ACCEL_GRID if accel == "grid" else api.ACCEL_LINEAR)
+    oids, ot = O.primary(O.scene(scene_id, True), O.camera(97, 61, double=True))
+    assert np.array_equal(ids, oids) and np.array_equal(bits(t), bits(ot))
+
+
+def test_double_grid_equals_scan_on_a_frame(renderer):
+    """1920x1080, scene 1 in double: grid == scan, bit for bit (2 M pixels, 4 spp)."""
+    import torch
+    renderer.upload_scene(rt.scene(1, double=True))
+    cam = rt.camera(1920, 1080, 4, 50, double=True)
+    a = torch.empty((1080, 1920, 3), dtype=torch.float64, device="cuda:0")
+    b = torch.empty_like(a)
+    renderer.render(cam, api.make_opts(accel=api.ACCEL_LINEAR), out=a)
+    seg = renderer.stats().segments
+    renderer.render(cam, api.make_opts(accel=api.ACCEL_GRID), out=b)
+    assert renderer.stats().segments == seg
+    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
 
 
 def test_render_is_deterministic_and_seeded(renderer):
@@ -994,7 +1013,9 @@ def test_auto_picks_grid_lbvh_linear(renderer):
     assert renderer.stats().accel_used == api.ACCEL_LBVH
     renderer.upload_scene(rt.scene(1, double=True))
     renderer.render(rt.camera(32, 20, 1, 4, double=True))
-    assert renderer.stats().accel_used == api.ACCEL_LINEAR
+    assert renderer.stats().accel_used == api.ACCEL_GRID            # double: float walk on the rounded ray, exact tests in double
+    with pytest.raises(rt.RtError):
+        renderer.render(rt.camera(32, 20, 1, 4, double=True), api.make_opts(accel=api.ACCEL_LBVH))   # the LBVH is a float structure
 
 
 @pytest.mark.parametrize("name", sorted(GRID_SCENES))

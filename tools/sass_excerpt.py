@@ -17,7 +17,10 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "raytracingincuda
 prefix = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "r02_sass")
 KERNELS = {"linear": "_ZN2rt15trace_kernel_pbIfLi0EEEvNS_9TraceArgsIT_EE", "grid": "_ZN2rt15trace_kernel_pbIfLi4EEEvNS_9TraceArgsIT_EE",
            "lbvh": "_ZN2rt15trace_kernel_pbIfLi1EEEvNS_9TraceArgsIT_EE", "finalize": "_ZN2rt15finalize_kernelIfEEvNS_10AccSourcesEyT_PS2_NS_12RowPlacementE"}
-lib_id = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:12]
+import ctypes
+_L = ctypes.CDLL(lib)
+_L.rt_kernel_build_id.restype = ctypes.c_char_p
+lib_id = _L.rt_kernel_build_id().decode()
 for tag, fun in KERNELS.items():
     text = subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], capture_output=True, text=True).stdout
     ins = [l for l in text.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
