@@ -309,6 +309,30 @@ def lib_id():
     return api.lib().rt_kernel_build_id().decode()
 
 
+def ncu_capture(kind):
+    """Pipe / issue utilisation of a trace kernel from the committed ncu capture (profiles/r02_pb_<kind>_key_metrics.csv), only
+    when the capture was taken with the library build that is loaded now (profiles/r02_capture_id.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_capture_id.json")) as f:
+            cap_id = json.load(f)["lib_id"]
+        if cap_id != lib_id():
+            return {"stale": f"profiles/r02_pb_{kind}_* were captured with build {cap_id}, this is {lib_id()}"}
+        out = {"source": f"profiles/r02_pb_{kind}_key_metrics.csv (ncu --set full, 1920x1080/16 spp, same library build)"}
+        names = {"sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fma_pipe_cycles_active_pct",
+                 "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+                 "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_instruction",
+                 "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+                 "launch__registers_per_thread": "registers"}
+        with open(os.path.join(ROOT, "profiles", f"r02_pb_{kind}_key_metrics.csv")) as f:
+            for row in f:
+                k, _, v = row.strip().split(",")
+                if k in names:
+                    out[names[k]] = round(float(v), 2)
+        return out
+    except Exception as e:
+        return {"unavailable": str(e)[:80]}
+
+
 def work_of(st, accel_name, n_slots, ms, peak):
     """Executed and reference-equivalent FP32 work of one trace launch from the kernel's own counters (rt_stats)."""
     executed = st.filter_tests * FLOP_PER_FILTER + st.sphere_tests * FLOP_PER_TEST + st.node_visits * FLOP_PER_NODE.get(accel_name, 0)
@@ -498,6 +522,7 @@ def run_b200_arm(args):
                 "note": ("the traversal kernels (grid / LBVH) are bound by divergence and dependent-load latency, not by the FP32 pipe; the "
                          "FP32-bound kernel of this path is the shared-memory linear scan: see `linear_scan`") if used != "linear" else
                         "FP32 issue bound: 7 FFMA2 + LDS.128 + 2 FSETP + 2 predicated OR per record of two tests",
+                "ncu": ncu_capture({"linear": "linear", "grid": "grid", "lbvh": "lbvh_s1"}.get(used, used)),
                 "traffic": None}
         # HBM traffic per trace launch: from the committed ncu pass of THIS library build when there is one, else what the
         # launch is known to move (accumulators zeroed, read-modify-written band by band through L2, read by finalize)
@@ -577,7 +602,7 @@ def run_b200_arm(args):
                            "peak": round(peak, 2), "frac": lin["frac_executed"],
                            "reference_equivalent_tflops": round(lin["segments_per_path"] * job.paths * lin["slots"] * FLOP_PER_TEST
                                                                 / (lin["kernel_ms"] * 1e-3) / 1e12, 3),
-                           "ncu": "profiles/r02_pb_linear_key_metrics.csv (sm__pipe_fma_cycles_active, issue slots, of this library build when lib_id matches)"}
+                           "ncu": ncu_capture("linear")}
         line["linear_scan"] = lin
         if len(job.slots) >= 256:
             line["accel_lbvh"] = quick(args.workload, "lbvh")

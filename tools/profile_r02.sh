@@ -30,6 +30,7 @@ for V in "linear:--accel linear" "grid:--accel grid" "lbvh_s1:--accel lbvh" "lbv
   echo "ncu $NAME rc=$?"
 done
 cp raytracingincuda_b200/librt_b200.so $O/librt_b200_$T.so        # the cubin the captures ran (tools/ncu_summarise.sh joins it by line)
+echo "{\"lib_id\": \"$LIBID\"}" > $O/${T}_capture_id.json
 ls -la $O/prof_${T}_pb*.ncu-rep
 # the reference's benchmark sweep (global_float_benchmark.sh:30-82) through tools/benchmark.py: the drop-in binary and the reference's
 # own GlobalFloat binary rebuilt for sm_100, same schema, so the rows can be joined
