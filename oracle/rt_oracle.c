@@ -195,16 +195,9 @@ int64_t orc_fix(double v) {                       /* v is the float or double ra
 
 /* Sample ranges per pixel: scheduling only (rt_num_chunks of the product; kept here so the host-logic tests can compare). */
 int orc_num_chunks(int width, int height, int spp) {
+    (void)width; (void)height;
     if (spp < 1) return 1;
-    int64_t npix = (int64_t)width * height;
-    int64_t c = ((int64_t)spp + 31) / 32;
-    if (npix > 0) {
-        int64_t want = (((int64_t)1 << 28) + npix - 1) / npix;
-        if (want > c) c = want;
-    }
-    if (c > spp) c = spp;
-    if (c > 4096) c = 4096;
-    return (int)c;
+    return spp > 65536 ? 65536 : spp;                 /* one sample per job */
 }
 
 int orc_quantise(float x) {

@@ -323,22 +323,15 @@ void rt_opts_default(rt_opts *opts) {
     opts->kernel = RT_KERNEL_MEGA;
 }
 
-// Sample ranges per pixel (scheduling only, see the header).  A launch ends when its last job ends, so long jobs leave the
-// machine draining: at config 4, 125-sample jobs cost a fixed 27 ms per launch and 32-sample jobs 10 ms; at config 2 -- a
-// 50-80 ms launch -- 25-sample jobs cost 3-9 % against 1-sample jobs (tools/tune_plan.py, profiles/logs/r02c_tune_plan.log).
-// The job fetch is one warp-aggregated atomic and a handful of multiply-highs, so short jobs are cheap: at most 32 samples
-// per job, and shorter ones until the frame has 2^28 jobs (config 4: 32 ranges of 31-32 samples; config 2: one sample per job).
+// Sample ranges per pixel (scheduling only, see the header): ONE sample per job up to 65 536 spp.  The lanes of a warp that
+// finish a path in the same turn claim consecutive jobs -- adjacent pixels, same sample index -- so their rays stay close to
+// each other; measured against 8-30 samples per job: config 4 1625 -> 1542 ms, config 5 1323 -> 1257 ms, config 2 39.8 -> 36.6 ms
+// (profiles/logs/r02w_job_granularity_cfg2.log, r02x_job_granularity_cfg4.log), and the drain at the end of a launch is one
+// sample long.
 int rt_num_chunks(int width, int height, int spp) {
+    (void)width; (void)height;
     if (spp < 1) return 1;
-    const int64_t npix = static_cast<int64_t>(width) * height;
-    int64_t c = (static_cast<int64_t>(spp) + 31) / 32;
-    if (npix > 0) {
-        const int64_t want = ((int64_t(1) << 28) + npix - 1) / npix;
-        if (want > c) c = want;
-    }
-    if (c > spp) c = spp;
-    if (c > 4096) c = 4096;
-    return static_cast<int>(c);
+    return spp > 65536 ? 65536 : spp;
 }
 
 int rt_partition_rows(int height, int tile_rows, int rank, int world, int32_t *rows, int capacity) {

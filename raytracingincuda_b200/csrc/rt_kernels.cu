@@ -48,20 +48,24 @@ template <typename T> struct DevCamera {
 
 // Job = (pixel, sample range).  The image does not depend on how the samples are cut into jobs (integer accumulation,
 // rt_device.cuh), so the cut is a pure scheduling choice (JobPlan, plan_jobs below): pixels are handed out in BANDS of rows
-// small enough that a band's accumulators stay in L2 while its jobs run, bottom band first; inside a band chunk-major.  All
-// bands but the last (the top rows of the frame) use `chunks[0]` sample ranges per pixel, the last band four times as many:
-// a launch ends when its last job ends, so the jobs that run while the machine drains are short ones on sky pixels.
+// small enough that a band's accumulators stay in L2 while its jobs run, bottom band first (the jobs that run while the machine
+// drains are sky pixels); inside a band chunk-major: all pixels for the first sample range, then for the second, ...
+// A job is ONE sample (spj = 1) unless spp is beyond 65 536: the lanes of a warp that finish a path in the same turn claim
+// consecutive jobs -- adjacent pixels, same sample index -- so their camera rays, their hits and their scattered rays stay
+// close to each other (same tile list, same material branch, same grid cells); with longer jobs the lanes of a warp drift
+// apart over the frame.  Measured (profiles/logs/r02w_*, r02x_*): config 4 1625 -> 1542 ms, config 5 1323 -> 1257 ms, config 2
+// 39.8 -> 36.6 ms against 8-30 samples per job -- and the drain at the end of the launch is one sample long.
 struct JobPlan {
     unsigned long long pix_local;      // pixels rendered by this launch
     unsigned long long total_jobs;
-    unsigned long long jobs_a;         // jobs of region A (all bands but the last); region B follows
-    unsigned long long band_jobs;      // band_pix * chunks[0]
-    unsigned long long rp_b;           // first reversed pixel of region B = (bands - 1) * band_pix
+    unsigned long long jobs_a;         // jobs of the full bands; the jobs of the last (partial) band follow
+    unsigned long long band_jobs;      // band_pix * chunks
+    unsigned long long rp_b;           // first reversed pixel of the last band = (bands - 1) * band_pix
     unsigned long long magic_band_jobs, magic_width;      // floor(2^64 / d) + 1 (0 encodes d == 1)
     unsigned long long magic_pix[2];                      // ... for band_pix / last_pix
     unsigned int band_pix, last_pix;   // pixels per full band / in the last band
-    int chunks[2];                     // sample ranges per pixel in region A / B
-    int spp_q[2], spp_r[2];            // s_count / chunks and s_count % chunks
+    int chunks;                        // sample ranges per pixel = ceil(s_count / spj)
+    int spj;                           // samples per job
     int s_begin, s_count;              // this launch traces samples [s_begin, s_begin + s_count) of every pixel
 };
 
@@ -291,7 +295,7 @@ template <typename T>
 __device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned long long job) {
     const JobPlan &P = A.plan;
     JobInfo J;
-    const int reg = job >= P.jobs_a;                                   // region B: the last band, finer sample ranges
+    const int reg = job >= P.jobs_a;                                   // the last band (the top rows; partial)
     unsigned long long r, rp0;
     if (reg) { r = job - P.jobs_a; rp0 = P.rp_b; }
     else {
@@ -307,11 +311,9 @@ __device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned lo
     J.pj = global_row(A, lr);
     J.pixel = (uint32_t)J.pj * (uint32_t)A.width + (uint32_t)J.pi;
     J.local = (uint32_t)lp;
-    // floor(c * S / C) without a 64-bit division
-    const int c = (int)cl, C = P.chunks[reg], q = P.spp_q[reg], rem = P.spp_r[reg];
-    J.sample = P.s_begin + c * q + (int)((unsigned)(c * rem) / (unsigned)C);
-    J.sample_end = P.s_begin + (c + 1) * q + (int)((unsigned)((c + 1) * rem) / (unsigned)C);
-    RT_CHECK(job < P.total_jobs && lp < P.pix_local && cl < (unsigned long long)C && r - cl * bp < bp, 201);
+    J.sample = P.s_begin + (int)cl * P.spj;
+    J.sample_end = min(J.sample + P.spj, P.s_begin + P.s_count);
+    RT_CHECK(job < P.total_jobs && lp < P.pix_local && cl < (unsigned long long)P.chunks && r - cl * bp < bp, 201);
     RT_CHECK(J.pi >= 0 && J.pi < A.width && J.pj >= 0 && J.pj < A.height, 202);
     RT_CHECK(J.sample >= P.s_begin && J.sample < J.sample_end && J.sample_end <= P.s_begin + P.s_count, 203);
     return J;
@@ -1241,10 +1243,9 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     P.s_count = s_count;
     if (P.pix_local == 0 || s_count <= 0) { P.total_jobs = 0; *out = P; return RT_OK; }
     if (P.pix_local > 0xffffffffull) return RT_EINVAL;                     // pixel indices are 32-bit (Philox counter word)
+    if ((long long)s_begin + s_count > (1ll << 30)) return RT_EINVAL;      // sample indices stay clear of int overflow
     int c_a = rt_num_chunks(width, rows_local, s_count);
     if (const char *e = getenv("RT_CHUNKS")) { const int v = atoi(e); if (v > 0) c_a = v < s_count ? v : s_count; }   // tuning knob
-    int tail_mult = 4;
-    if (const char *e = getenv("RT_TAIL_MULT")) { const int v = atoi(e); if (v > 0) tail_mult = v; }
     // bands: as many rows as keep the band's accumulators (24 B per pixel) within 8 MB of L2
     long long band_rows = (8ll << 20) / (24ll * width);
     if (const char *e = getenv("RT_BAND_ROWS")) { const int v = atoi(e); if (v > 0) band_rows = v; }
@@ -1256,17 +1257,15 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     P.last_pix = (unsigned int)(P.pix_local - (bands - 1) * band_pix);
     P.rp_b = (bands - 1) * band_pix;
     for (;; c_a = (c_a + 1) / 2) {
-        long long c_b = (long long)c_a * tail_mult;
-        if (c_b > s_count) c_b = s_count;
-        P.chunks[0] = c_a; P.chunks[1] = (int)c_b;
-        P.band_jobs = band_pix * (unsigned long long)c_a;
+        P.spj = (s_count + c_a - 1) / c_a;
+        P.chunks = (s_count + P.spj - 1) / P.spj;
+        P.band_jobs = band_pix * (unsigned long long)P.chunks;
         P.jobs_a = (bands - 1) * P.band_jobs;
-        P.total_jobs = P.jobs_a + (unsigned long long)P.last_pix * (unsigned long long)c_b;
+        P.total_jobs = P.jobs_a + (unsigned long long)P.last_pix * (unsigned long long)P.chunks;
         // multiply-high division is exact while dividend * divisor < 2^64; keep a wide margin.  Gigantic renders get longer jobs.
-        if ((long double)P.total_jobs * (long double)P.band_jobs < 9.0e18L && P.chunks[1] <= 16384) break;
+        if ((long double)P.total_jobs * (long double)P.band_jobs < 9.0e18L) break;
         if (c_a == 1) return RT_EINVAL;
     }
-    for (int r = 0; r < 2; ++r) { P.spp_q[r] = s_count / P.chunks[r]; P.spp_r[r] = s_count % P.chunks[r]; }
     auto magic = [](unsigned long long d) { return d > 1 ? ~0ull / d + 1ull : 0ull; };
     P.magic_band_jobs = magic(P.band_jobs);
     P.magic_pix[0] = magic(band_pix);
@@ -1305,7 +1304,7 @@ int fill_args(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int
     A.acc = acc;
     A.queue = ctx->queue;
     RT_CUDA(cudaMemsetAsync(ctx->queue, 0, QUEUE_WORDS * sizeof(unsigned long long), ctx->stream));
-    ctx->stats.chunks = A.plan.chunks[0];
+    ctx->stats.chunks = A.plan.chunks;
     return RT_OK;
 }
 

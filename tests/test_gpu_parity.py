@@ -178,7 +178,7 @@ def test_spp_split_equals_whole_frame(renderer, world):
     assert np.array_equal(bits(whole), bits(ref))
 
 
-@pytest.mark.parametrize("knobs", [{"RT_CHUNKS": "1"}, {"RT_CHUNKS": "7", "RT_TAIL_MULT": "3"}, {"RT_BAND_ROWS": "1"},
+@pytest.mark.parametrize("knobs", [{"RT_CHUNKS": "1"}, {"RT_CHUNKS": "7"}, {"RT_CHUNKS": "3", "RT_BAND_ROWS": "2"}, {"RT_BAND_ROWS": "1"},
                                    {"RT_BAND_ROWS": "5", "RT_CHUNKS": "40"}])
 def test_image_does_not_depend_on_the_job_partition(renderer, knobs, monkeypatch):
     """Integer accumulation: however the scheduler cuts pixels into bands and samples into jobs (tuning knobs of

@@ -98,7 +98,7 @@ def test_partitions():
         rt.partition_rows(10, 8, 2, 2)
     with pytest.raises(rt.RtError):
         rt.partition_samples(10, 2, 2)
-    assert rt.num_chunks(3840, 2160, 1000) == 33 and rt.num_chunks(320, 192, 4096) == 4096
+    assert rt.num_chunks(3840, 2160, 1000) == 1000 and rt.num_chunks(320, 192, 4096) == 4096 and rt.num_chunks(8, 8, 10 ** 6) == 65536
     for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 10), (320, 192, 4096), (320, 192, 5), (8, 8, 100000),
                       (7680, 4320, 100000), (640, 360, 17), (3840, 2160, 256), (97, 61, 12)]:
         assert rt.num_chunks(w, h, spp) == O.num_chunks(w, h, spp), (w, h, spp)

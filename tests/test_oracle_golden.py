@@ -135,34 +135,25 @@ def test_hit_world_edge_cases():
 
 
 def test_job_granularity():
-    """Sample ranges per pixel are scheduling only (the accumulation is an integer sum): jobs of at most 32 samples, more
-    and shorter jobs on small frames, never more ranges than samples."""
-    assert O.num_chunks(3840, 2160, 1000) == 33              # 30-31 samples per job
-    assert O.num_chunks(1920, 1080, 100) == 100              # a short launch: one sample per job
+    """Sample ranges per pixel are scheduling only (the accumulation is an integer sum): one sample per job up to 65 536 spp."""
+    assert O.num_chunks(3840, 2160, 1000) == 1000
+    assert O.num_chunks(1920, 1080, 100) == 100
     assert O.num_chunks(320, 192, 10) == 10
-    assert O.num_chunks(320, 192, 4096) == 4096
-    assert O.num_chunks(3840, 2160, 256) == 33
-    assert O.num_chunks(7680, 4320, 100000) == 3125
     assert O.num_chunks(320, 192, 5) == 5
-    assert O.num_chunks(8, 8, 100000) == 4096
-    for spp in (9, 17, 100, 1000):
-        c = O.num_chunks(640, 360, spp)
-        edges = [k * spp // c for k in range(c + 1)]
-        assert edges[0] == 0 and edges[-1] == spp and all(b > a for a, b in zip(edges, edges[1:]))
+    assert O.num_chunks(8, 8, 100000) == 65536
+    assert O.num_chunks(8, 8, 0) == 1
 
 
-def test_chunk_edges_without_the_wide_division():
-    """The kernels compute a range's first sample as c*(S // C) + c*(S % C) // C in 32-bit arithmetic (rt_kernels.cu
-    decode_job); it must equal floor(c * S / C), and c * (S % C) must stay below 2^31 -- also for the four-times finer
-    ranges of the last band."""
-    for w, h, spp in [(3840, 2160, 1000), (1920, 1080, 100), (320, 192, 4096), (8, 8, 100000), (640, 360, 17), (97, 61, 1023),
-                      (7680, 4320, 100000), (64, 40, 2147483647)]:
-        for mult in (1, 4):
-            C = min(O.num_chunks(w, h, spp) * mult, spp)
-            q, r = divmod(spp, C)
-            assert C <= 16384 and (C + 1) * r < 2 ** 31
-            for c in list(range(0, C + 1, max(1, C // 37))) + [C]:
-                assert c * q + (c * r) // C == (c * spp) // C
+def test_sample_ranges_tile_the_samples():
+    """The kernels' job decode (rt_kernels.cu decode_job): spj = ceil(S / C) samples per job, C' = ceil(S / spj) ranges,
+    range c = [c * spj, min((c + 1) * spj, S)) -- the ranges tile [0, S) for every S and every requested C (tuning knob)."""
+    for S in (1, 2, 9, 17, 100, 1000, 65536, 100000, 2147483647):
+        for C in (1, 2, 7, 33, 100, 1000, 65536):
+            c_req = min(C, S)
+            spj = (S + c_req - 1) // c_req
+            chunks = (S + spj - 1) // spj
+            assert chunks <= c_req and (chunks - 1) * spj < S <= chunks * spj
+            assert chunks * spj < 2 ** 32
 
 
 def test_fixed_point_accumulation():
