@@ -64,6 +64,8 @@ struct JobPlan {
     unsigned long long magic_band_jobs, magic_width;      // floor(2^64 / d) + 1 (0 encodes d == 1)
     unsigned long long magic_pix[2];                      // ... for band_pix / last_pix
     unsigned int band_pix, last_pix;   // pixels per full band / in the last band
+    unsigned int tiles_per_row;        // > 0: pixels are numbered in 8 x 4 tiles (width % 8 == 0, rows % 4 == 0), else row-major
+    unsigned long long magic_tpr;
     int chunks;                        // sample ranges per pixel = ceil(s_count / spj)
     int spj;                           // samples per job
     int s_begin, s_count;              // this launch traces samples [s_begin, s_begin + s_count) of every pixel
@@ -86,6 +88,7 @@ template <typename T> struct TraceArgs {
     const unsigned int *bins;          // trace_kernel_pb only: per-tile candidate lists of the camera rays (rt_primary_bins.cuh)
     int tiles_x, tiles;
     int pb_rounds, pb_min;             // camera-ray rounds per loop turn; rounds after the first need this many fresh lanes
+    int pb_cohort;                     // lanes out of work claim new jobs only when this many can claim together (1: at once)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -306,14 +309,25 @@ __device__ __forceinline__ JobInfo decode_job(const TraceArgs<T> &A, unsigned lo
     const unsigned long long bp = reg ? P.last_pix : P.band_pix;
     const unsigned long long cl = div_magic(r, P.magic_pix[reg]);
     const unsigned long long lp = P.pix_local - 1ull - (rp0 + (r - cl * bp));   // bands are counted from the bottom of the frame
-    const int lr = (int)div_magic(lp, P.magic_width);
-    J.pi = (int)(lp - (unsigned long long)lr * A.width);
+    int lr;
+    if (P.tiles_per_row) {
+        // 8 x 4 pixel tiles, row-major inside a tile and across tiles: the lanes that claim together cover a compact block
+        // (one tile list, neighbouring rays) instead of a strip of a row
+        const unsigned long long tile = lp >> 5;
+        const unsigned int w = (unsigned int)lp & 31u;
+        const unsigned long long ty = div_magic(tile, P.magic_tpr);
+        J.pi = (int)((tile - ty * P.tiles_per_row) * 8ull) + (int)(w & 7u);
+        lr = (int)(ty * 4ull) + (int)(w >> 3);
+    } else {
+        lr = (int)div_magic(lp, P.magic_width);
+        J.pi = (int)(lp - (unsigned long long)lr * A.width);
+    }
     J.pj = global_row(A, lr);
     J.pixel = (uint32_t)J.pj * (uint32_t)A.width + (uint32_t)J.pi;
-    J.local = (uint32_t)lp;
+    J.local = (uint32_t)lr * (uint32_t)A.width + (uint32_t)J.pi;
     J.sample = P.s_begin + (int)cl * P.spj;
     J.sample_end = min(J.sample + P.spj, P.s_begin + P.s_count);
-    RT_CHECK(job < P.total_jobs && lp < P.pix_local && cl < (unsigned long long)P.chunks && r - cl * bp < bp, 201);
+    RT_CHECK(job < P.total_jobs && lp < P.pix_local && J.local < P.pix_local && cl < (unsigned long long)P.chunks && r - cl * bp < bp, 201);
     RT_CHECK(J.pi >= 0 && J.pi < A.width && J.pj >= 0 && J.pj < A.height, 202);
     RT_CHECK(J.sample >= P.s_begin && J.sample < J.sample_end && J.sample_end <= P.s_begin + P.s_count, 203);
     return J;
@@ -1251,6 +1265,10 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     if (const char *e = getenv("RT_BAND_ROWS")) { const int v = atoi(e); if (v > 0) band_rows = v; }
     if (band_rows < 1) band_rows = 1;
     if (band_rows > rows_local) band_rows = rows_local;
+    // 8 x 4 tile numbering needs whole tiles: bands of a multiple of 4 rows
+    const bool tiled = width % 8 == 0 && rows_local % 4 == 0 && !getenv("RT_NO_TILE_ORDER");
+    if (tiled) { band_rows = band_rows >= 4 ? band_rows / 4 * 4 : 4; }
+    P.tiles_per_row = tiled ? (unsigned int)(width / 8) : 0u;
     const unsigned long long band_pix = (unsigned long long)band_rows * width;
     const unsigned long long bands = (P.pix_local + band_pix - 1) / band_pix;
     P.band_pix = (unsigned int)band_pix;
@@ -1271,6 +1289,7 @@ int plan_jobs(int width, int rows_local, int s_begin, int s_count, JobPlan *out)
     P.magic_pix[0] = magic(band_pix);
     P.magic_pix[1] = magic(P.last_pix);
     P.magic_width = magic((unsigned long long)width);
+    P.magic_tpr = magic((unsigned long long)P.tiles_per_row);
     *out = P;
     return RT_OK;
 }
@@ -1290,6 +1309,14 @@ int fill_args(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int
     A.pb_min = 1;
     if (const char *e = getenv("RT_PB_ROUNDS")) A.pb_rounds = atoi(e) > 0 ? atoi(e) : A.pb_rounds;       // tuning knobs
     if (const char *e = getenv("RT_PB_MIN")) A.pb_min = atoi(e);
+    // lanes out of work claim together (adjacent pixels): measured 1 / 4 / 8 / 12 / 16 / 24 lanes -- grid 36.21 / 35.96 / 35.63 /
+    // 35.66 / 36.21 / 40.2 ms, LBVH (99 860 slots) 43.02 / 42.79 / 42.93 / 43.99 / 46.35 / 58.25, scan 80.06 / 79.94 / 80.43 /
+    // 82.12 / 85.46 / 103.5 (profiles/logs/r02z_cohort.log): waiting costs the scan more than coherence gives it
+    {
+        const int acc = resolve_accel(ctx, o);
+        A.pb_cohort = acc == RT_ACCEL_GRID ? 8 : (acc == RT_ACCEL_LBVH ? 4 : 1);
+    }
+    if (const char *e = getenv("RT_PB_COHORT")) A.pb_cohort = atoi(e);
     A.cam = to_dev<T>(cam);
     A.scene = ctx->blob;
     A.keys = philox_keys(o.seed);

@@ -278,7 +278,10 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
         // ---- A: camera rays through the tile lists ----
 #pragma unroll 1
         for (int round = 0; round < A.pb_rounds; ++round) {
-            const unsigned want = __ballot_sync(FULL, state == NEED_JOB);
+            unsigned want = __ballot_sync(FULL, state == NEED_JOB);
+            // cohorts: lanes that claim together get adjacent pixels (coherent rays); with pb_cohort > 1 the lanes that ran out of
+            // work wait until that many of them can claim together -- unless nobody else in the warp has work left
+            if (A.pb_cohort > 1 && __popc(want) < A.pb_cohort && __any_sync(FULL, state == ACTIVE)) want = 0u;
             if (want) {
                 const unsigned long long claimed = claim_job(A, lane, want);
                 if (state == NEED_JOB) {

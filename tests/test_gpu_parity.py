@@ -179,18 +179,20 @@ def test_spp_split_equals_whole_frame(renderer, world):
 
 
 @pytest.mark.parametrize("knobs", [{"RT_CHUNKS": "1"}, {"RT_CHUNKS": "7"}, {"RT_CHUNKS": "3", "RT_BAND_ROWS": "2"}, {"RT_BAND_ROWS": "1"},
-                                   {"RT_BAND_ROWS": "5", "RT_CHUNKS": "40"}])
+                                   {"RT_BAND_ROWS": "5", "RT_CHUNKS": "40"}, {"RT_NO_TILE_ORDER": "1"}, {"RT_PB_COHORT": "16"}])
 def test_image_does_not_depend_on_the_job_partition(renderer, knobs, monkeypatch):
     """Integer accumulation: however the scheduler cuts pixels into bands and samples into jobs (tuning knobs of
     plan_jobs), the frame is the same bit for bit."""
     renderer.upload_scene(rt.scene(3))
-    cam = rt.camera(70, 33, 40, 12)
+    cam = rt.camera(72, 36, 40, 12)                  # 72 x 36: pixels are numbered in 8 x 4 tiles by default
     base = renderer.render(cam)
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     img = renderer.render(cam)
-    assert renderer.stats().paths == 70 * 33 * 40
+    assert renderer.stats().paths == 72 * 36 * 40
     assert np.array_equal(bits(img), bits(base))
+    ref, _ = O.render(O.scene(3), O.camera(72, 36, 40, 12))
+    assert np.array_equal(bits(base), bits(ref))
 
 
 @pytest.mark.parametrize("scene_id", [1, 2, 3])
