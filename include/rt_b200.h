@@ -158,9 +158,9 @@ int rt_camera_init64(rt_camera64 *cam, int width, int height, int spp, int max_d
 
 void rt_opts_default(rt_opts *opts);
 
-/* Sample ranges per pixel the scheduler cuts `spp` samples into (jobs of about 32 samples).  Scheduling only: radiance is
- * accumulated in 64-bit fixed point with integer atomics, so the image depends on neither this number, nor the launch
- * shape, nor the GPU count. */
+/* Sample ranges per pixel the scheduler cuts `spp` samples into (one sample per job up to 65 536 spp).  Scheduling only:
+ * radiance is accumulated in 64-bit fixed point with integer atomics, so the image depends on neither this number, nor the
+ * launch shape, nor the GPU count. */
 int rt_num_chunks(int width, int height, int spp);
 
 /* Rows rendered by `rank` of `world` under RT_SPLIT_ROWS, ascending.  Returns the count; writes
