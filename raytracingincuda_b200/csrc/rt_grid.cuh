@@ -1,9 +1,8 @@
-// rt_grid.cuh -- uniform-grid closest hit for fields of equal spheres on a plane (the reference's scenes, BASELINE configs
-// 2-5).  EXPERIMENTAL in round 1: the algorithm is validated on the CPU against the oracle (tools/grid_model.py states it in
-// float32 operation by operation, tests/test_grid_model.py checks it on logged path segments), this CUDA transcription has
-// has had ONE hardware run (round 1, commit "RT_ACCEL_GRID (experimental ...": 9 gated parity tests green, scene 1 at config 2
-// 49.3 ms against 57.7 ms through the LBVH, but 225 ms against 47 ms on the 99 860-slot scene); the per-step inflation below
-// was added after that run and has only been checked in the model -- RT_ACCEL_GRID stays refused unless RT_ENABLE_GRID=1.
+// rt_grid.cuh -- uniform-grid closest hit for fields of similar spheres on a plane (the reference's scenes, BASELINE configs
+// 2-5): what RT_ACCEL_AUTO picks for them since round 2.  The algorithm is stated operation by operation in float32 in
+// tools/grid_model.py and checked on the CPU against the oracle's hit_world on logged path segments (tests/test_grid_model.py);
+// on the GPU the kernel returns the linear scan's (slot id, t) bit for bit (tests/test_gpu_parity.py: primary passes and whole
+// frames on scenes from 40 to 99 860 slots, random fields with odd-sized, negative-radius and duplicate spheres, float and double).
 //
 // A 2-D grid over the two long axes of the small spheres holds, per cell, the slots whose padded footprint overlaps the
 // cell; a ray walks the cells of its projection (Amanatides-Woo) inside the inflated box of those spheres and runs the

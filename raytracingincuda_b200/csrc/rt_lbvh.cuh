@@ -220,6 +220,14 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
     tv.a = dot3(d, d);
     tv.hit.t = N::inf();
     tv.hit.id = -1;
+    tv.node = -1;
+    tv.sp = 0;
+    // A ray whose |d|^2 is +inf or NaN hits nothing in the reference's arithmetic (GF hittable.h:40-66): both roots are
+    // (h -/+ sqrt(disc)) / a with a = +inf or NaN, i.e. +-0 when the numerator is finite and NaN otherwise, and neither passes
+    // `tmin < root`.  Such rays exist -- a path that lands on the zero-radius slot gets n = (p - c) * (1/0), and config 5 traces
+    // 2 x 10^9 paths -- and with 1/d = +-0 every slab test below answers "inside": one lane then walked all 199 719 nodes and
+    // tested all 99 860 leaves, ~100 ms at the end of a launch (profiles/logs/r02af_long_traversals.log).  Same answer, no walk.
+    if (!(tv.a < N::inf())) return;
     // the spheres outside the tree -- and the tree itself when it is a single sphere -- through ONE copy of the exact test
     // (the traversal kernels are instruction-fetch bound: every inlined copy of the sqrt/div sequences costs I-cache)
     const int n_direct = bv.nbig + (bv.m == 1 ? 1 : 0);
@@ -229,8 +237,6 @@ __device__ __forceinline__ void bvh_start(const BvhView &bv, const Vec3<float> &
         bvh_test_sphere(__ldg(big ? bv.big_geom + b : bv.geom), __ldg(big ? bv.big_slot + b : bv.slot), o, d, tv.a, tv.hit);
     }
     n_tests += n_direct;
-    tv.node = -1;
-    tv.sp = 0;
     if (bv.m <= 1) return;
     tv.inv.x = __frcp_rn(d.x); tv.inv.y = __frcp_rn(d.y); tv.inv.z = __frcp_rn(d.z);      // == 1.0f / x, the shorter sequence
     tv.node = 0;

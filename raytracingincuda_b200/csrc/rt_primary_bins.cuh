@@ -251,6 +251,9 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
     hit.id = -1;
     int pi = 0, pj = 0, sample = 0, sample_end = 0, depth = 0;
     uint32_t pixel = 0, local = 0, tile = 0;
+#ifdef RT_DIAG_LONG_TRAVERSAL
+    int diag_visits = 0;
+#endif
 
     auto end_black = [&]() {
         ++s_cnt[1][threadIdx.x];
@@ -352,12 +355,22 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
             if (state == ACTIVE && phase == RAY) {
                 bvh_start<RAYD>(A.bvh, ps.o, ps.d, tv, n_tests);
                 phase = FLY;
+#ifdef RT_DIAG_LONG_TRAVERSAL
+                diag_visits = 0;
+#endif
             }
 #pragma unroll 1
             for (int step = 0; step < A.bvh_steps; ++step) {
                 const int flying_lanes = __popc(__ballot_sync(FULL, tv.node >= 0));
                 if (flying_lanes == 0 || (flying_lanes < A.bvh_min_active && step > 0)) break;
                 if (tv.node >= 0) bvh_step<RAYD>(A.bvh, ps.o, ps.d, tv, bvh_stack, n_nodes, n_tests);
+#ifdef RT_DIAG_LONG_TRAVERSAL
+                // diagnostic build only: which rays make very long traversals?
+                if (tv.node >= 0 && ++diag_visits % RT_DIAG_LONG_TRAVERSAL == 0)
+                    printf("long traversal: %d visits pixel (%d,%d) sample %d depth %d o %.9g %.9g %.9g d %.9g %.9g %.9g best t %g id %d sp %d\n", diag_visits,
+                           pi, pj, sample, depth, (double)ps.o.x, (double)ps.o.y, (double)ps.o.z, (double)ps.d.x, (double)ps.d.y, (double)ps.d.z,
+                           (double)tv.hit.t, tv.hit.id, tv.sp);
+#endif
             }
             s_cnt[2][threadIdx.x] += n_nodes;
             s_cnt[3][threadIdx.x] += n_tests;

@@ -554,6 +554,31 @@ def test_lbvh_mid_size_scene_equals_linear_scan(renderer):
     assert np.array_equal(bits(a), bits(b))
 
 
+@pytest.mark.parametrize("half", [11, 30])
+def test_rays_with_non_finite_directions_hit_nothing_in_every_structure(renderer, half):
+    """|d|^2 = +inf or NaN: the reference's roots are (h -/+ sqrt(disc)) / a = +-0 or NaN, never > tmin (GF hittable.h:40-66), so the
+    scan reports no hit.  bvh_start answers that without walking the tree -- such a ray passes every slab test and used to visit
+    every node (config 5: one lane, 199 719 nodes, ~100 ms at the end of the launch).  Columns of the probe camera: finite rays,
+    |d| ~ 1e25 (a overflows), infinite components, NaN components."""
+    renderer.upload_scene(rt.scene(1) if half == 11 else rt.scene_scaled(half))
+    cam = rt.camera(64, 24)
+    first = None
+    for i, du in enumerate(((cam.du[0], cam.du[1], cam.du[2]), (1e25, 0.0, -1e24), (float("inf"), 0.0, 0.0), (float("nan"), 1.0, 0.0))):
+        for k in range(3):
+            cam.du[k] = du[k]
+        ids, t = renderer.primary_hits(cam)
+        for accel in (api.ACCEL_LBVH, api.ACCEL_GRID):
+            aids, at = renderer.primary_hits(cam, accel=accel)
+            assert np.array_equal(ids, aids) and np.array_equal(bits(t), bits(at)), (i, accel)
+        if i == 0:
+            first = ids
+            assert (ids >= 0).any()
+        else:
+            if i == 1:
+                assert np.array_equal(ids[:, 0], first[:, 0])              # 0 * 1e25 = 0: column 0 is still the finite camera ray
+            assert (ids[:, 1:] == -1).all() and np.isinf(t[:, 1:]).all()   # from column 1 on, |d|^2 is inf or NaN in every row
+
+
 def test_lbvh_100k_scene_primary_vs_oracle(renderer):
     """BASELINE config 5 scene (99 860 slots): LBVH primary (slot id, t) against the oracle's
     linear hit_world, bit for bit."""
