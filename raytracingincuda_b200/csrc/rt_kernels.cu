@@ -174,19 +174,70 @@ template <> __device__ __forceinline__ void sky<double>(double puy, double &r, d
     b = __dadd_rn(a, t1);
 }
 
-// One bounce: hit record (GF hittable.h:58-63) + the material switch of GF camera.h:92-108.
-// `ph` is opened on (pixel, sample, depth+1): block 0 feeds the Schlick uniform of a dielectric (word 0; double: words 0, 1)
-// or the first random_unit_vector candidate (GF vec3.h:117-127; one candidate per block -- float -- or per two blocks --
-// double), later blocks the later candidates.  HAVE0 (what every kernel uses): `ph` already holds block 0; otherwise it is
-// computed at the one Philox site of the candidate loop (smaller, but measured 5 % slower).
+// The point random_unit_vector (GF vec3.h:117-127) tries with one Philox block, and whether it accepts it
+// (unit_min < |c|^2 <= 1); float only -- a double candidate takes two blocks (scatter's own loop).
+__device__ __forceinline__ bool ball_candidate(const Philox &ph, Vec3<float> &c) {
+    using N = Num<float>;
+    c.x = N::fma(N::uniform(ph.w[0], 0), 2.0f, -1.0f);
+    c.y = N::fma(N::uniform(ph.w[1], 0), 2.0f, -1.0f);
+    c.z = N::fma(N::uniform(ph.w[2], 0), 2.0f, -1.0f);
+    const float l2 = dot3(c, c);
+    return N::unit_min() < l2 && l2 <= 1.0f;
+}
+
+// Warp-cooperative tail of random_unit_vector's rejection loop (float kernels; call with all 32 lanes).  A lane whose first
+// candidate (block 0 of its own (pixel, sample, dimension) counter) was rejected enters with need = true; the accepted
+// candidate is the one of the SMALLEST block index that passes, exactly as the sequential loop finds it.  Left to itself the
+// loop runs at 6-8 active threads (half of the searching lanes drop out per trip, the warp waits for the unluckiest: 11 % of the
+// grid kernel's instructions); here every lane of the warp -- searching, shading a dielectric, or idle -- computes one block per
+// trip for the first searching lane at or above it: lane f is served by the lanes (previous searching lane, f], helper L tries
+// block next_f + (f - L), and f takes the passing helper closest to itself.  Two trips on average instead of four to five.
+__device__ __forceinline__ void coop_unit_vector(const PhiloxKeys &keys, bool need, uint32_t c0, uint32_t c1, uint32_t c2, Vec3<float> &c) {
+    const int lane = threadIdx.x & 31;
+    uint32_t next = 1u;
+    unsigned searching = __ballot_sync(FULL, need);
+    while (searching) {
+        const unsigned up = searching >> lane;                    // bit 0 = this lane
+        const int dist = up ? __ffs(up) - 1 : 0;
+        const int f = lane + dist;
+        const uint32_t h0 = __shfl_sync(FULL, c0, f), h1 = __shfl_sync(FULL, c1, f), h2 = __shfl_sync(FULL, c2, f);
+        const uint32_t hk = __shfl_sync(FULL, next, f) + (uint32_t)dist;
+        Vec3<float> hc;
+        hc.x = hc.y = hc.z = 0.0f;
+        bool ok = false;
+        if (up) {
+            Philox ph;
+            ph.open(keys, h0, h1, h2);
+            ph.block(hk);
+            ok = ball_candidate(ph, hc);
+        }
+        const unsigned passed = __ballot_sync(FULL, ok);
+        int src = lane;
+        bool found = false;
+        if (need) {
+            const unsigned below = searching & ((1u << lane) - 1u);
+            const int prev = below ? 31 - __clz(below) : -1;      // the previous searching lane
+            const unsigned upto_me = 0xffffffffu >> (31 - lane), upto_prev = prev >= 0 ? 0xffffffffu >> (31 - prev) : 0u;
+            const unsigned mine = passed & upto_me & ~upto_prev;
+            if (mine) { src = 31 - __clz(mine); found = true; need = false; }
+            else next += (uint32_t)(lane - prev);
+        }
+        const float sx = __shfl_sync(FULL, hc.x, src), sy = __shfl_sync(FULL, hc.y, src), sz = __shfl_sync(FULL, hc.z, src);
+        if (found) { c.x = sx; c.y = sy; c.z = sz; }
+        searching = __ballot_sync(FULL, need);
+    }
+}
+
+// One bounce: hit record (GF hittable.h:58-63) + the material switch of GF camera.h:92-108, given the random numbers of the
+// bounce: `schlick_u` for a dielectric, the accepted candidate `cand` of random_unit_vector (not yet normalised) otherwise.
 // Returns false when the path is absorbed (metal scattered below the surface, GF material.h:58).
-template <typename T, bool HAVE0 = true>
-__device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hit, Philox &ph, PathState<T> &ps) {
+template <typename T>
+__device__ __forceinline__ bool scatter_with(const SceneView<T> &sc, const Hit<T> &hit, int type, T schlick_u, const Vec3<T> &cand,
+                                             PathState<T> &ps) {
     using N = Num<T>;
     RT_CHECK(hit.id >= 0 && hit.id < sc.n, 302);
     const typename N::vec4 s = sc.geom[hit.id];
     const typename N::vec4 m = sc.matl[hit.id];
-    const int type = sc.type[hit.id];
     const Vec3<T> o = ps.o, d = ps.d;
     Vec3<T> p;
     p.x = N::fma(hit.t, d.x, o.x); p.y = N::fma(hit.t, d.y, o.y); p.z = N::fma(hit.t, d.z, o.z);
@@ -195,33 +246,6 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
     n.x = N::mul(N::sub(p.x, s.x), inv_r); n.y = N::mul(N::sub(p.y, s.y), inv_r); n.z = N::mul(N::sub(p.z, s.z), inv_r);
     const bool front = dot3(d, n) < T(0);
     if (!front) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
-
-    // random numbers of this bounce: the Schlick uniform, or the first candidate in the unit ball that passes
-    // unit_min < |v|^2 <= 1, normalised (random_unit_vector, GF vec3.h:117-127)
-    Vec3<T> uv;
-    uv.x = uv.y = uv.z = T(0);
-    T schlick_u = T(0);
-    for (uint32_t k = 0;; ++k) {
-        T ux, uy, uz;
-        if (N::words_per_uniform == 1) {
-            if (!HAVE0 || k > 0) ph.block(k);
-            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], 0); break; }
-            ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
-        } else {
-            if (!HAVE0 || k > 0) ph.block(2u * k);
-            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], ph.w[1]); break; }
-            ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
-            ph.block(2u * k + 1u);
-            uz = N::uniform(ph.w[0], ph.w[1]);
-        }
-        uv.x = N::fma(ux, T(2), T(-1)); uv.y = N::fma(uy, T(2), T(-1)); uv.z = N::fma(uz, T(2), T(-1));
-        const T l2 = dot3(uv, uv);
-        if (N::unit_min() < l2 && l2 <= T(1)) {
-            const T inv = N::rcp(N::sqrt(l2));
-            uv.x = N::mul(inv, uv.x); uv.y = N::mul(inv, uv.y); uv.z = N::mul(inv, uv.z);
-            break;
-        }
-    }
 
     Vec3<T> nd;
     if (type == RT_DIELECTRIC) {
@@ -255,6 +279,11 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
             nd.x = N::fma(k, n.x, perp.x); nd.y = N::fma(k, n.y, perp.y); nd.z = N::fma(k, n.z, perp.z);
         }
     } else {
+        Vec3<T> uv;
+        {
+            const T inv = N::rcp(N::sqrt(dot3(cand, cand)));      // unit_vector of the accepted candidate (GF vec3.h:126)
+            uv.x = N::mul(inv, cand.x); uv.y = N::mul(inv, cand.y); uv.z = N::mul(inv, cand.z);
+        }
         if (type == RT_LAMBERTIAN) {
             // lambertian_scatter (GF material.h:38-49)
             nd.x = N::add(n.x, uv.x); nd.y = N::add(n.y, uv.y); nd.z = N::add(n.z, uv.z);
@@ -275,6 +304,38 @@ __device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hi
     ps.o = p;
     ps.d = nd;
     return true;
+}
+
+// scatter with the sequential draw.  `ph` is opened on (pixel, sample, depth+1): block 0 feeds the Schlick uniform of a
+// dielectric (word 0; double: words 0, 1) or the first random_unit_vector candidate (one candidate per block -- float -- or
+// per two blocks -- double), later blocks the later candidates.  HAVE0: `ph` already holds block 0; otherwise it is computed
+// at the one Philox site of the candidate loop (smaller, but measured 5 % slower).
+template <typename T, bool HAVE0 = true>
+__device__ __forceinline__ bool scatter(const SceneView<T> &sc, const Hit<T> &hit, Philox &ph, PathState<T> &ps) {
+    using N = Num<T>;
+    RT_CHECK(hit.id >= 0 && hit.id < sc.n, 302);
+    const int type = sc.type[hit.id];
+    Vec3<T> cand;
+    cand.x = cand.y = cand.z = T(1);
+    T schlick_u = T(0);
+    for (uint32_t k = 0;; ++k) {
+        T ux, uy, uz;
+        if (N::words_per_uniform == 1) {
+            if (!HAVE0 || k > 0) ph.block(k);
+            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], 0); break; }
+            ux = N::uniform(ph.w[0], 0); uy = N::uniform(ph.w[1], 0); uz = N::uniform(ph.w[2], 0);
+        } else {
+            if (!HAVE0 || k > 0) ph.block(2u * k);
+            if (type == RT_DIELECTRIC) { schlick_u = N::uniform(ph.w[0], ph.w[1]); break; }
+            ux = N::uniform(ph.w[0], ph.w[1]); uy = N::uniform(ph.w[2], ph.w[3]);
+            ph.block(2u * k + 1u);
+            uz = N::uniform(ph.w[0], ph.w[1]);
+        }
+        cand.x = N::fma(ux, T(2), T(-1)); cand.y = N::fma(uy, T(2), T(-1)); cand.z = N::fma(uz, T(2), T(-1));
+        const T l2 = dot3(cand, cand);
+        if (N::unit_min() < l2 && l2 <= T(1)) break;
+    }
+    return scatter_with<T>(sc, hit, type, schlick_u, cand, ps);
 }
 
 template <typename T>

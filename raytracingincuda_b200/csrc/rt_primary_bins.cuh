@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(128) bin_kernel_bvh(const __grid_constant__ De
 #ifndef RT_TRACE_MIN_BLOCKS_GRID
 #define RT_TRACE_MIN_BLOCKS_GRID 4
 #endif
+#ifndef RT_COOP_UNIT
+#define RT_COOP_UNIT 1                 // float kernels: warp-cooperative random_unit_vector (coop_unit_vector, rt_kernels.cu)
+#endif
 template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK, sizeof(T) == 4 ? (ACCEL == RT_ACCEL_LINEAR ? RT_TRACE_MIN_BLOCKS : (ACCEL == RT_ACCEL_GRID ? RT_TRACE_MIN_BLOCKS_GRID : RT_TRACE_MIN_BLOCKS_LBVH)) : 2)
 trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
@@ -340,7 +343,30 @@ trace_kernel_pb(const __grid_constant__ TraceArgs<T> A) {
         if (__all_sync(FULL, state == DEAD)) break;
 
         // ---- B: shade the pending hits (GF camera.h:92-117) ----
-        if (state == ACTIVE && phase == HIT) {
+        if constexpr (sizeof(T) == 4 && RT_COOP_UNIT) {
+            // the whole warp looks for the unit vectors of the lanes whose first candidate was rejected (coop_unit_vector)
+            const bool shade = (state == ACTIVE && phase == HIT);
+            int type = RT_DIELECTRIC;
+            T schlick_u = T(0);
+            Vec3<T> cand;
+            cand.x = cand.y = cand.z = T(1);
+            bool need = false;
+            if (shade) {
+                Philox ph;
+                ph.open(A.keys, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
+                ph.block(0);
+                RT_CHECK(hit.id >= 0 && hit.id < sc.n, 302);
+                type = sc.type[hit.id];
+                if (type == RT_DIELECTRIC) schlick_u = N::uniform(ph.w[0], 0);
+                else need = !ball_candidate(ph, cand);
+            }
+            coop_unit_vector(A.keys, need, pixel, (uint32_t)sample, (uint32_t)(depth + 1), cand);
+            if (shade) {
+                const bool alive = scatter_with<T>(sc, hit, type, schlick_u, cand, ps);
+                if (!alive || ++depth >= A.max_depth) end_black();                // GF camera.h:117 / :84,127 -> black
+                else phase = RAY;
+            }
+        } else if (state == ACTIVE && phase == HIT) {
             Philox ph;
             ph.open(A.keys, pixel, (uint32_t)sample, (uint32_t)(depth + 1));
             ph.block(0);
