@@ -87,7 +87,8 @@ enum { RT_SPLIT_NONE = 0, RT_SPLIT_ROWS = 1, RT_SPLIT_SPP = 2 };
  *           8 192 slots: the walk runs in float on the rounded ray, the exact tests in double; RT_EINVAL if the scene is not
  *           such a field: fewer than two similar spheres or more than 64 of a very different size);
  *   AUTO    (default) LINEAR below 32 slots and for the wavefront kernel; otherwise GRID when the scene is a planar field of
- *           similar spheres of moderate extent (the reference's scenes), else LBVH (float) or LINEAR (double). */
+ *           similar spheres of moderate extent (the reference's scenes, the scaled field up to 99 860 slots), else LBVH (float)
+ *           or LINEAR (double). */
 enum { RT_ACCEL_LINEAR = 0, RT_ACCEL_LBVH = 1, RT_ACCEL_AUTO = 2, RT_ACCEL_GRID = 4 };
 enum { RT_KERNEL_MEGA = 0, RT_KERNEL_WAVEFRONT = 1 };
 enum { RT_PBINS_AUTO = 0, RT_PBINS_OFF = 1, RT_PBINS_ON = 2 };   /* AUTO: on wherever it applies */

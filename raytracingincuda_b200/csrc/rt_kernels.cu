@@ -1244,16 +1244,18 @@ int build_grid(rt_ctx *ctx) {
     ctx->grid_ready = true;
     ctx->grid_usable = true;
     // RT_ACCEL_AUTO picks the grid for a planar field of moderate extent: the slab axis is thin against the cell size, and the
-    // float-noise inflation delta of a sphere half a diagonal away from the ray origin stays within the registration padding,
-    // so that most steps look at their own cell only.  Measured at 1920x1080 (tools/time_accels.py, profiles/logs/
-    // r02e_time_accels.log; grid / LBVH / scan): 40 slots 19.2 / 20.2 / 21.5 ms, 125 slots 25.0 / 25.2 / 29.8, 488 slots
-    // 47.9 / 51.6 / 80.6, 3 604 slots 59.6 / 71.5 / 656, 14 404 slots 45.8 / 58.2, 99 860 slots (far cells need a ring of
-    // neighbours) 44.1 / 42.1 -- the one case left to the LBVH, which is also the structure BASELINE config 5 names.
+    // float-noise inflation delta of a sphere half a diagonal away from the ray origin stays within half a cell, so that a step
+    // looks at its own cell and -- far from the origin only -- at one ring of neighbours.  Measured at 1920x1080
+    // (tools/time_accels.py, tools/ab_variants.sh; grid / LBVH / scan): 40 slots 17.7 / 19.2 / 21.2 ms, 125 slots 20.1 / 23.9 /
+    // 29.4, 488 slots 34.5 / 48.3 / 79.8, 3 604 slots 45 / 72 / 630, 14 404 slots 35.6 / 57.5, 99 860 slots (far cells need the
+    // ring) 39.7 / 41.9, and at 3840x2160 / 128 spp 565 / 620 ms (profiles/logs/r02ag_cfg5_modes.log, r02ah_coop_ab.log).  Until
+    // the last measurement the 99 860-slot field was left to the LBVH (delta within the registration padding was the rule); larger
+    // fields than that have not been measured and still are.
     double diag2 = 0.0;
     for (int q = 0; q < 3; ++q) diag2 += (hi3[q] - lo3[q]) * (hi3[q] - lo3[q]);
     const double reach = 0.5 * std::sqrt(diag2);
     const double delta_half = (std::sqrt((double)BVH_KEPS * reach * reach + r_min * r_min) - r_min) * 1.001 + 1e-7 + 4.8e-7 * 2.0 * reach;
-    ctx->grid_auto = (hi3[av] - lo3[av]) <= 4.0 * (double)G.h && delta_half <= (double)G.pad && std::isfinite(delta_half);
+    ctx->grid_auto = (hi3[av] - lo3[av]) <= 4.0 * (double)G.h && delta_half <= 0.5 * (double)G.h && std::isfinite(delta_half);
     ctx->grid_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
     return RT_OK;
 }

@@ -1021,11 +1021,12 @@ def test_grid_is_refused_for_a_scene_that_is_not_a_field(renderer):
 
 
 def test_auto_picks_grid_lbvh_linear(renderer):
-    """RT_ACCEL_AUTO: the planar fields of the reference's scenes -> grid; the 99 860-slot field (far cells need rings: BASELINE
-    config 5 names the LBVH) and a 3-D soup -> LBVH; tiny and double scenes -> linear scan."""
+    """RT_ACCEL_AUTO: planar fields of similar spheres -> grid, from the reference's scenes up to the 99 860-slot field of BASELINE
+    config 5 (the grid is 6-9 % ahead of the LBVH there; bench.py still reports config 5 through the LBVH the config names);
+    a 3-D soup -> LBVH; tiny scenes -> linear scan."""
     cam = rt.camera(32, 20, 1, 4)
     for slots, want in ((rt.scene(1), api.ACCEL_GRID), (rt.scene(3), api.ACCEL_GRID), (rt.scene(2), api.ACCEL_GRID),
-                        (rt.scene(1)[:20].copy(), api.ACCEL_LINEAR), (rt.scene_scaled(158), api.ACCEL_LBVH),
+                        (rt.scene(1)[:20].copy(), api.ACCEL_LINEAR), (rt.scene_scaled(158), api.ACCEL_GRID),
                         (rt.scene_scaled(12), api.ACCEL_GRID), (rt.scene_scaled(60), api.ACCEL_GRID)):
         renderer.upload_scene(slots)
         renderer.render(cam)
