@@ -20,6 +20,9 @@
 
 namespace rt {
 
+#ifndef RT_GRID_RING_EDGE
+#define RT_GRID_RING_EDGE 1
+#endif
 struct GridView {
     const unsigned int *start;    // [nu * nw + 1] first item of each cell
     const unsigned int *items;    // slots, cell by cell
@@ -49,12 +52,34 @@ __device__ __forceinline__ float hit_t_up(double t) { return __double2float_ru(t
 
 // Cold path of a step whose inflation reaches beyond its own cell (cells hundreds of units from the ray origin): every cell
 // within k rings.  Out of line: the walk's hot loop stays small (the kernel is instruction-fetch bound).
+// Consecutive ring steps overlap in all but their leading edge: after a step that tested the whole block around (cu', cw') with
+// the same k, a move by one cell only brings the 2k+1 cells of the new column (or row) -- the others have been tested, and
+// testing a sphere twice changes nothing (its first root > tmin is a function of the ray; the minimum has already seen it).
+// `prev` remembers the last ring step (cell, k, step number); on the 99 860-slot scene the ring loops were 29 % of the
+// kernel's instructions at 3 active threads (profiles/r02_pb_grid_100k_by_source_line.txt of build 7799f1692b92).
+struct RingPrev { int cu, cw, k, step; };
 template <typename T>
-__device__ __noinline__ void grid_ring_tests(const typename Num<T>::vec4 *__restrict__ geom, int cu, int cw, int k, Vec3<T> o, Vec3<T> d, T a,
-                                             Hit<T> &hit, unsigned &n_tests) {
+__device__ __noinline__ void grid_ring_tests(const typename Num<T>::vec4 *__restrict__ geom, int cu, int cw, int k, int step, RingPrev &prev,
+                                             Vec3<T> o, Vec3<T> d, T a, Hit<T> &hit, unsigned &n_tests) {
     const GridView &g = g_grid;
-    for (int b = max(cw - k, 0); b <= min(cw + k, g.nw - 1); ++b)
-        for (int c = max(cu - k, 0); c <= min(cu + k, g.nu - 1); ++c) {
+    int b0 = max(cw - k, 0), b1 = min(cw + k, g.nw - 1), c0 = max(cu - k, 0), c1 = min(cu + k, g.nu - 1);
+#if RT_GRID_RING_EDGE
+    const bool chained = prev.step == step + 1 && prev.k == k;        // steps_left counts down: the previous step was a ring step too
+    const int du = chained ? cu - prev.cu : 0, dw = chained ? cw - prev.cw : 0;
+    prev.cu = cu; prev.cw = cw; prev.k = k; prev.step = step;
+    if (chained) {
+        if (du == 0 && dw == 0) return;                               // clamped at the border: the same block
+        if (dw == 0 && (du == 1 || du == -1)) {
+            c0 = c1 = cu + du * k;
+            if (c0 < 0 || c0 >= g.nu) return;
+        } else if (du == 0 && (dw == 1 || dw == -1)) {
+            b0 = b1 = cw + dw * k;
+            if (b0 < 0 || b0 >= g.nw) return;
+        }
+    }
+#endif
+    for (int b = b0; b <= b1; ++b)
+        for (int c = c0; c <= c1; ++c) {
             const int cell = b * g.nu + c;
             RT_CHECK(cell >= 0 && cell < g.nu * g.nw, 601);
             const unsigned int e0 = __ldg(g.start + cell), e1 = __ldg(g.start + cell + 1);
@@ -90,6 +115,8 @@ __device__ __forceinline__ Hit<T> grid_closest_hit(const GridView &g, const type
     float t1 = 0.0f, iu_inv = 0.0f, iw_inv = 0.0f, delta = 0.0f;
     int iu = 0, iw = 0, su = 0, sw = 0, k_global = 0, steps_left = -1;        // steps_left < 0: the big list is being tested
     unsigned int e = 0u, e1 = (unsigned int)g.nbig;
+    RingPrev ring_prev;                                                       // the other fields are read only after a ring step set them
+    ring_prev.step = -2;                                                      // no ring step yet (steps_left + 1 is never -2)
     for (;;) {
         n_tests += e1 - e;
         const unsigned int *list = steps_left < 0 ? reinterpret_cast<const unsigned int *>(g.big_slot) : g.items;
@@ -168,7 +195,7 @@ __device__ __forceinline__ Hit<T> grid_closest_hit(const GridView &g, const type
             k = ds <= g.half_pad ? 0 : min((int)fminf(ceilf((ds - g.half_pad) / g.h), 8192.0f), k_global);
         }
         if (k > 0) {
-            grid_ring_tests<T>(geom, cu, cw, k, oT, dT, aT, hit, n_tests);
+            grid_ring_tests<T>(geom, cu, cw, k, steps_left, ring_prev, oT, dT, aT, hit, n_tests);
             e = e1 = 0u;
         } else {
             const int cell = cw * g.nu + cu;

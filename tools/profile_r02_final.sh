@@ -37,7 +37,7 @@ for WL in cfg2 cfg4; do for ACC in auto linear; do cp $O/${T}_bench_${WL}_${ACC}
 ls -la $O/prof_${T}_pb*.ncu-rep
 mkdir -p $O/benchmarks
 python tools/benchmark.py --exe $B --out $O/benchmarks/b200_float.csv --scenes 1 --sizes 320x192,480x288,640x384,960x576,1280x768,1920x1080 --samples 10,100 --bounces 25 --threads 8 --runs 3 > /dev/null 2>&1
-python tools/benchmark.py --exe oracle/_ref/global-float-cuda-raytrace --out $O/benchmarks/reference_global_float_sm100.csv --scenes 1 --sizes 320x192,480x288,640x384,960x576,1280x768,1920x1080 --samples 10,100 --bounces 25 --threads 8 --runs 3 > /dev/null 2>&1
+[ "${REF_SWEEP:-1}" = 1 ] && python tools/benchmark.py --exe oracle/_ref/global-float-cuda-raytrace --out $O/benchmarks/reference_global_float_sm100.csv --scenes 1 --sizes 320x192,480x288,640x384,960x576,1280x768,1920x1080 --samples 10,100 --bounces 25 --threads 8 --runs 3 > /dev/null 2>&1
 echo "benchmark sweeps rc=$?"; cat $O/benchmarks/b200_float_avg.csv | head -20
 python bench.py > $O/bench_${T}_cfg4.json 2> $O/bench_${T}_cfg4.err; echo "bench cfg4 rc=$?"
 python bench.py --impl reference --steps 1 --warmup 0 > $O/bench_${T}_ref.json 2> $O/bench_${T}_ref.err; echo "bench ref rc=$?"
