@@ -127,3 +127,41 @@ def test_far_origins_widen_the_walk():
         assert s == want_s and (want_s < 0 or np.float32(t).view(np.uint32) == want_t.view(np.uint32)), (o, d, s, want_s)
         n_hit += want_s >= 0 and want_s not in set(G.big.tolist())
     assert n_hit > 50
+
+
+def test_ring_steps_need_only_their_leading_edge():
+    """grid_ring_tests (rt_grid.cuh, final round-2 build): after a ring step with the same k, a move by one cell brings the
+    2k+1 cells of the new column or row -- the rest of the block was looked at by the previous step.  Same tested slots and
+    the same hit as looking at the whole block every step, with a fraction of the look-ups: rays from far origins across
+    scene 1 (several rings along the whole walk) and logged segments of a 40 004-slot field (rings for the far cells only)."""
+    rng = np.random.default_rng(9)
+    cases = []
+    s1 = O.scene(1)
+    G1 = GM.Grid(s1)
+    for _ in range(150):
+        ang, dist = rng.uniform(0, 2 * np.pi), rng.uniform(150, 900)
+        o = np.array([dist * np.cos(ang), rng.uniform(0.05, 3.0), dist * np.sin(ang)], dtype=np.float32)
+        target = np.array([rng.uniform(-11, 11), rng.uniform(0.0, 0.4), rng.uniform(-11, 11)], dtype=np.float32)
+        cases.append((s1, G1, o, ((target - o) * np.float32(rng.uniform(0.2, 2.0))).astype(np.float32)))
+    big = O.scene_scaled(100)
+    Gb = GM.Grid(big)
+    for row in logged_segments(big, O.camera(640, 360, 1000, 50), 40, seed=17):
+        cases.append((big, Gb, row[0:3], row[3:6]))
+    # camera rays towards the horizon of the large field: hundreds of steps, the far ones with rings
+    for _ in range(40):
+        o = np.array([13.0, 2.0, 3.0], dtype=np.float32)
+        target = np.array([rng.uniform(-95, -40), rng.uniform(0.0, 0.4), rng.uniform(-95, 95)], dtype=np.float32)
+        cases.append((big, Gb, o, (target - o).astype(np.float32)))
+    look = {True: 0, False: 0}
+    ring_rays = 0
+    for slots, G, o, d in cases:
+        big_t, _ = closest_among(slots, G.big, o, d)
+        res = {}
+        for edge in (True, False):
+            st = {}
+            t, s, tested, cells = GM.candidates(G, o, d, big_t, lambda idx: closest_among(slots, idx, o, d), ring_edge=edge, stats=st)
+            res[edge] = (np.float32(t).view(np.uint32), s, frozenset(tested), cells)
+            look[edge] += st.get("lookups", 0)
+        assert res[True] == res[False], (o, d)
+        ring_rays += res[True][3] > 0
+    assert ring_rays > 100 and look[True] < 0.6 * look[False], look
