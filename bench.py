@@ -333,6 +333,47 @@ def ncu_capture(kind):
         return {"unavailable": str(e)[:80]}
 
 
+def framebuffer_roofline(r, job, peaks, peaks_src, reps=20):
+    """finalize_flat_kernel on the job's frame: 24 B of int64 accumulators read + 12 B of float frame written per pixel."""
+    import torch
+    from raytracingincuda_b200 import api
+    import raytracingincuda_b200 as rt
+    cam1 = rt.camera(job.W, job.H, 1, job.depth)
+    acc = torch.empty((job.W * job.H * 3,), dtype=torch.int64, device=job.frame.device)
+    r.render_partials(cam1, api.make_opts(), acc)              # real radiance sums of one sample per pixel
+    ms = []
+    for _ in range(reps + 3):
+        r.finalize(cam1, acc, out=job.frame)
+        ms.append(r.last_finalize_ms)
+    med = statistics.median(ms[3:])
+    os.environ["RT_FINALIZE_BY_PIXEL"] = "1"                   # the four-pixels-per-thread kernel this one replaced (still used for row placement)
+    try:
+        old = []
+        for _ in range(8):
+            r.finalize(cam1, acc, out=job.frame)
+            old.append(r.last_finalize_ms)
+    finally:
+        del os.environ["RT_FINALIZE_BY_PIXEL"]
+    nbytes = job.W * job.H * (24 + 12)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"bound": "hbm", "kernel": "finalize_flat_kernel<float>", "unit": "GB/s", "bytes_per_launch": nbytes, "ms": round(med, 4),
+           "ms_min": round(min(ms[3:]), 4), "launches_timed": reps, "achieved": round(nbytes / (med * 1e-3) / 1e9, 1), "peak": peak,
+           "frac": round(nbytes / (med * 1e-3) / 1e9 / peak, 4), "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
+           "l2": f"{job.W * job.H * 24} B read + {job.W * job.H * 12} B written per launch: larger than the 126 MB L2 at 4K", "traffic": None,
+           "by_pixel_kernel_ms": round(statistics.median(old[3:]), 4)}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_bench_kernel_traffic.json")) as f:
+            cap = json.load(f)
+        if cap.get("lib_id") == lib_id():
+            k = next((v for name, v in cap.get("cfg4", {}).items() if "finalize" in name), None)
+            if k and (job.W, job.H) == (3840, 2160):
+                out["traffic"] = int(k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"])
+                out["traffic_source"] = "profiles/r02_bench_kernel_traffic.json (ncu dram__bytes_read+write per launch, same library build)"
+    except Exception:
+        pass
+    return out
+
+
 def work_of(st, accel_name, n_slots, ms, peak):
     """Executed and reference-equivalent FP32 work of one trace launch from the kernel's own counters (rt_stats)."""
     executed = st.filter_tests * FLOP_PER_FILTER + st.sphere_tests * FLOP_PER_TEST + st.node_visits * FLOP_PER_NODE.get(accel_name, 0)
@@ -615,6 +656,12 @@ def run_b200_arm(args):
                     line["accel_grid"] = quick(args.workload, "grid")
                 except Exception as e:
                     line["accel_grid"] = {"error": str(e)[:100]}
+        # the one HBM-bound kernel of the path: accumulators -> gamma-encoded frame (north star (d), "achieved HBM GB/s for the
+        # framebuffer"); timed live through rt_finalize on a buffer of the headline frame's size, input + output larger than L2
+        try:
+            line["framebuffer"] = framebuffer_roofline(r, job, peaks, peaks_src)
+        except Exception as e:
+            line["framebuffer"] = {"error": str(e)[:120]}
         if args.workload == "cfg4":
             cfgs = {}
             # config 5 names its structure ("on-GPU LBVH"): it is timed through RT_ACCEL_LBVH; what the library's default

@@ -637,6 +637,60 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ A
     }
 }
 
+// The same conversion when the rows stay where they are (one GPU, the spp split, rt_finalize[_sum]): value c of the frame
+// depends on accumulator c alone, so the frame is converted as a flat array -- lane i of a warp reads the i-th 16-byte pair of
+// sums and writes the i-th pair of values.  finalize_kernel's 96-byte groups per thread put the 16-byte loads of a warp 96 bytes
+// apart (every load instruction touches 32 sectors for 512 useful bytes): 0.108 ms = 2.8 TB/s for a 4K frame; here every load
+// and store instruction covers whole lines.  HBM-bound: 24 B read per pixel and source + 12 B written.
+constexpr int FINALIZE_FLAT_UNROLL = 4;
+template <typename T> struct Pair2;
+template <> struct Pair2<float> { using type = float2; };
+template <> struct Pair2<double> { using type = double2; };
+template <typename T>
+__device__ __forceinline__ T encode_value(long long sum, T scale) {
+    using N = Num<T>;
+    const T c = N::mul(unfix<T>(sum), scale);                              // GF camera.h:167
+    return c > T(0) ? N::sqrt(c) : T(0);                                    // GF color.h:10-13
+}
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_flat_kernel(const __grid_constant__ AccSources src, unsigned long long vals, T scale,
+                                                            T *__restrict__ out) {
+    constexpr int U = FINALIZE_FLAT_UNROLL;
+    const unsigned long long pairs = vals >> 1;
+    const unsigned long long base = (unsigned long long)blockIdx.x * (U * 256ull) + threadIdx.x;
+    long long sx[U], sy[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sx[u] = sy[u] = 0;
+    for (int g = 0; g < src.n; ++g) {
+        const int4 *a = reinterpret_cast<const int4 *>(src.p[g]);              // one 16-byte load per pair of sums
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned long long j = base + (unsigned long long)u * 256ull;
+            if (j < pairs) {
+                const int4 q = __ldg(a + j);
+                sx[u] += (long long)(((unsigned long long)(unsigned int)q.y << 32) | (unsigned int)q.x);
+                sy[u] += (long long)(((unsigned long long)(unsigned int)q.w << 32) | (unsigned int)q.z);
+            }
+        }
+    }
+    typename Pair2<T>::type *o2 = reinterpret_cast<typename Pair2<T>::type *>(out);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned long long j = base + (unsigned long long)u * 256ull;
+        if (j < pairs) {
+            typename Pair2<T>::type v;
+            v.x = encode_value<T>(sx[u], scale);
+            v.y = encode_value<T>(sy[u], scale);
+            o2[j] = v;
+        }
+    }
+    if ((vals & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) {                 // an odd number of pixels: the last value
+        long long t = 0;
+        for (int g = 0; g < src.n; ++g) t += src.p[g][vals - 1];
+        out[vals - 1] = encode_value<T>(t, scale);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T, int ACCEL>
 __global__ void __launch_bounds__(TRACE_BLOCK) primary_kernel(const __grid_constant__ DevCamera<T> cam,
@@ -1584,6 +1638,15 @@ int trace(rt_ctx *ctx, const Cam &cam, const rt_opts &o, int rows_local, int s_b
 template <typename T>
 int finalize(rt_ctx *ctx, const AccSources &src, unsigned long long pix, T scale, T *out_dev, RowPlacement rp = RowPlacement{0, 1, 0, 1}) {
     if (pix == 0) return RT_OK;
+    if (rp.world <= 1 && (reinterpret_cast<uintptr_t>(out_dev) & (2 * sizeof(T) - 1)) == 0 && !getenv("RT_FINALIZE_BY_PIXEL")) {
+        // no row placement: the frame is a flat array of 3 * pix values, each a function of its own accumulator
+        const unsigned long long vals = 3ull * pix, pairs = vals >> 1;
+        const unsigned grid = (unsigned)((pairs + FINALIZE_FLAT_UNROLL * 256ull - 1) / (FINALIZE_FLAT_UNROLL * 256ull));
+        finalize_flat_kernel<T><<<grid ? grid : 1u, 256, 0, ctx->stream>>>(src, vals, scale, out_dev);
+        RT_CUDA(cudaGetLastError());
+        ctx->stats.launches += 1;
+        return RT_OK;
+    }
     const unsigned long long quads = (pix + 3) / 4;
     const unsigned grid = (unsigned)((quads + 255) / 256);
     finalize_kernel<T><<<grid, 256, 0, ctx->stream>>>(src, pix, scale, out_dev, rp);

@@ -90,6 +90,33 @@ def test_render_bit_exact_vs_oracle(renderer, scene_id, w, h, spp, depth, accel)
     assert len(mism) == 0, f"{len(mism)} differing channels, first {mism[:3]}"
 
 
+@pytest.mark.parametrize("w,h", [(64, 40), (33, 17), (5, 1), (7, 3)])
+def test_flat_and_by_pixel_finalize_kernels_write_the_same_frame(renderer, w, h):
+    """finalize_flat_kernel (rows stay where they are: pairs of values, coalesced) against finalize_kernel (four pixels per
+    thread; still used for row placement and for frames that are not 8-byte aligned), even and odd pixel counts, and both
+    against the oracle's frame."""
+    import torch
+    renderer.upload_scene(rt.scene(1))
+    cam = rt.camera(w, h, 5, 8)
+    ref, _ = O.render(O.scene(1), O.camera(w, h, 5, 8))
+    flat = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+    renderer.render(cam, out=flat)
+    backing = torch.full((h * w * 3 + 1,), -1.0, dtype=torch.float32, device="cuda:0")
+    odd = backing[1:].view(h, w, 3)                                  # 4 bytes off a 16-byte boundary: the by-pixel kernel
+    assert odd.data_ptr() % 8 == 4
+    renderer.render(cam, out=odd)
+    os.environ["RT_FINALIZE_BY_PIXEL"] = "1"
+    try:
+        forced = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        renderer.render(cam, out=forced)
+    finally:
+        del os.environ["RT_FINALIZE_BY_PIXEL"]
+    torch.cuda.synchronize()
+    assert float(backing[0]) == -1.0
+    for img in (flat, odd, forced):
+        assert np.array_equal(bits(img.cpu().numpy()), bits(ref))
+
+
 @pytest.mark.parametrize("accel", ["linear", "grid"])
 @pytest.mark.parametrize("scene_id,w,h,spp,depth", [(1, 32, 20, 6, 25), (2, 48, 32, 9, 50), (3, 40, 24, 8, 50), (1, 21, 13, 40, 50)])
 def test_render_bit_exact_vs_oracle_double(renderer, scene_id, w, h, spp, depth, accel):

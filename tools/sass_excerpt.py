@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "raytracingincuda_b200", "librt_b200.so")
 prefix = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "r02_sass")
 KERNELS = {"linear": "_ZN2rt15trace_kernel_pbIfLi0EEEvNS_9TraceArgsIT_EE", "grid": "_ZN2rt15trace_kernel_pbIfLi4EEEvNS_9TraceArgsIT_EE",
-           "lbvh": "_ZN2rt15trace_kernel_pbIfLi1EEEvNS_9TraceArgsIT_EE", "finalize": "_ZN2rt15finalize_kernelIfEEvNS_10AccSourcesEyT_PS2_NS_12RowPlacementE"}
+           "lbvh": "_ZN2rt15trace_kernel_pbIfLi1EEEvNS_9TraceArgsIT_EE", "finalize": "_ZN2rt20finalize_flat_kernelIfEEvNS_10AccSourcesEyT_PS2_"}
 import ctypes
 _L = ctypes.CDLL(lib)
 _L.rt_kernel_build_id.restype = ctypes.c_char_p
