@@ -359,7 +359,8 @@ def framebuffer_roofline(r, job, peaks, peaks_src, reps=20):
     out = {"bound": "hbm", "kernel": "finalize_flat_kernel<float>", "unit": "GB/s", "bytes_per_launch": nbytes, "ms": round(med, 4),
            "ms_min": round(min(ms[3:]), 4), "launches_timed": reps, "achieved": round(nbytes / (med * 1e-3) / 1e9, 1), "peak": peak,
            "frac": round(nbytes / (med * 1e-3) / 1e9 / peak, 4), "peak_source": f"{peaks_src} MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
-           "l2": f"{job.W * job.H * 24} B read + {job.W * job.H * 12} B written per launch: larger than the 126 MB L2 at 4K", "traffic": None,
+           "l2": f"{job.W * job.H * 24} B read + {job.W * job.H * 12} B written per launch: " +
+                 ("larger than the 126 MB L2" if nbytes > 126e6 else "fits the 126 MB L2 (not an HBM measurement at this frame size)"), "traffic": None,
            "by_pixel_kernel_ms": round(statistics.median(old[3:]), 4)}
     try:
         with open(os.path.join(ROOT, "profiles", "r02_bench_kernel_traffic.json")) as f:
