@@ -134,6 +134,29 @@ def test_hit_world_edge_cases():
     assert hit == -1                                       # empty world
 
 
+def test_rays_with_non_finite_length_hit_nothing():
+    """|d|^2 = +inf or NaN: both roots (h -/+ sqrt(disc)) / a are +-0 or NaN, and `surrounds` (GF interval.h:21-23) rejects
+    both -- whatever the origin, also inside the ground sphere.  rt_lbvh.cuh's bvh_start relies on it to skip the tree walk
+    (such a ray passes every slab test); the GPU suite checks the three structures against each other on such rays."""
+    L = O.lib()
+    slots = O.scene(1)
+    rng = np.random.default_rng(4)
+    t = C.c_float()
+    bad = [(np.inf, -np.inf, np.inf), (np.inf, 0.0, 0.0), (0.0, -np.inf, 0.5), (1e25, 0.0, -1e24), (-3e19, 3e19, 1.0),
+           (np.nan, 1.0, 0.0), (np.nan, np.nan, np.nan), (np.inf, np.nan, -1.0)]
+    origins = [(13.0, 2.0, 3.0), (0.278919101, -0.306284547, 0.473543942), (0.0, 1.0, 0.0), (4.0, 1.0, 0.0), (0.0, -500.0, 0.0)]
+    origins += [tuple(rng.uniform(-11, 11, 3)) for _ in range(20)]
+    for o in origins:
+        for d in bad:
+            with np.errstate(all="ignore"):
+                hit = L.orc_hit_world(slots.ctypes.data, len(slots), (C.c_float * 3)(*o), (C.c_float * 3)(*d), C.c_float(0.001),
+                                      C.c_float(np.inf), C.byref(t))
+            assert hit == -1, (o, d, hit, t.value)
+    # the same origins do hit something with an ordinary direction (the ground, if nothing else)
+    assert L.orc_hit_world(slots.ctypes.data, len(slots), (C.c_float * 3)(13.0, 2.0, 3.0), (C.c_float * 3)(-1.0, -0.2, -0.3),
+                           C.c_float(0.001), C.c_float(np.inf), C.byref(t)) >= 0
+
+
 def test_job_granularity():
     """Sample ranges per pixel are scheduling only (the accumulation is an integer sum): one sample per job up to 65 536 spp."""
     assert O.num_chunks(3840, 2160, 1000) == 1000
